@@ -1,0 +1,162 @@
+// TEST INFRASTRUCTURE — not part of the product.
+//
+// C-ABI shim over the UNMODIFIED reference classes (ParameterFactory /
+// ParameterContainer, /root/reference/src/include/*.h).  It is compiled by
+// oracle/Makefile together with the reference's own .cpp files, where they
+// lie under /root/reference, into oracle/_ref/libpspace_ref{,_z}.so.
+// It exists so that Python (ctypes) can drive the real reference in this
+// container to (a) pin the restated oracle (oracle/pspace_oracle.c) and
+// (b) generate the golden vectors under tests/golden/, and (c) serve as the
+// "reference" CPU baseline of bench.py.
+//
+// The projection loops below restate, over the reference's own per-call
+// primitives, the loops of the reference *caller*
+//   examples/stacs/cpp/TACSStochasticElement.cpp:283-311 (vector: scale = basis(i,zq)*wq)
+//   examples/stacs/cpp/TACSStochasticElement.cpp:380-414 (matrix: scale = basis(i,zq)*basis(j,zq)*wq)
+// with the (un-vendored) TACS element call replaced by the synthetic
+// per-point block  A[c] += scale*J_q[c].
+//
+// scalars cross the ABI as double (real build) or interleaved (re,im) pairs
+// (USE_COMPLEX build), i.e. a `scalar*` is passed as `double*`.
+#include <thread>
+#include <vector>
+#include <cstring>
+#include "scalar.h"
+#include "ParameterFactory.h"
+#include "ParameterContainer.h"
+
+struct RefHandle {
+  ParameterFactory *factory;      // one factory per container (ids restart at 0)
+  ParameterContainer *pc;
+  std::vector<AbstractParameter*> params;
+  int nvars;
+};
+
+static inline scalar mk(const double *p, int i){
+#ifdef USE_COMPLEX
+  return scalar(p[2*i], p[2*i+1]);
+#else
+  return p[i];
+#endif
+}
+
+extern "C" {
+
+int refshim_is_complex(){
+#ifdef USE_COMPLEX
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+// kinds: 0 normal(mu,sigma) 1 uniform(a,b) 2 exponential(mu,beta)
+void *refshim_create(int nvars, const int *kinds, const double *p1, const double *p2,
+                     const int *dmax, int basis_type){
+  RefHandle *h = new RefHandle();
+  h->factory = new ParameterFactory();
+  h->pc = new ParameterContainer(basis_type, 0);
+  h->nvars = nvars;
+  for (int d = 0; d < nvars; d++){
+    AbstractParameter *p = 0;
+    if (kinds[d] == 0)      p = h->factory->createNormalParameter(mk(p1,d), mk(p2,d), dmax[d]);
+    else if (kinds[d] == 1) p = h->factory->createUniformParameter(mk(p1,d), mk(p2,d), dmax[d]);
+    else                    p = h->factory->createExponentialParameter(mk(p1,d), mk(p2,d), dmax[d]);
+    h->params.push_back(p);
+    h->pc->addParameter(p);
+  }
+  return h;
+}
+void refshim_initialize(void *hh){ ((RefHandle*)hh)->pc->initialize(); }
+void refshim_initialize_basis(void *hh, const int *pmax){ ((RefHandle*)hh)->pc->initializeBasis(pmax); }
+void refshim_initialize_quadrature(void *hh, const int *nq){ ((RefHandle*)hh)->pc->initializeQuadrature(nq); }
+int refshim_num_basis(void *hh){ return ((RefHandle*)hh)->pc->getNumBasisTerms(); }
+int refshim_num_quad(void *hh){ return ((RefHandle*)hh)->pc->getNumQuadraturePoints(); }
+int refshim_num_params(void *hh){ return ((RefHandle*)hh)->pc->getNumParameters(); }
+
+// degrees out[N][nvars]
+void refshim_degrees(void *hh, int *out){
+  RefHandle *h = (RefHandle*)hh;
+  int N = h->pc->getNumBasisTerms();
+  for (int k = 0; k < N; k++) h->pc->getBasisParamDeg(k, out + (size_t)k*h->nvars);
+}
+void refshim_max_degrees(void *hh, int *out){ ((RefHandle*)hh)->pc->getBasisParamMaxDeg(out); }
+
+// Z[Q][nvars], Y[Q][nvars], W[Q] (point-major, as quadrature(q,zq,yq) hands them out)
+void refshim_grid(void *hh, double *Z, double *Y, double *W){
+  RefHandle *h = (RefHandle*)hh;
+  int Q = h->pc->getNumQuadraturePoints(), nv = h->nvars;
+  scalar *z = (scalar*)Z, *y = (scalar*)Y, *w = (scalar*)W;
+  for (int q = 0; q < Q; q++) w[q] = h->pc->quadrature(q, z + (size_t)q*nv, y + (size_t)q*nv);
+}
+
+// psi[k][p] = basis(k, z_p), z[npts][nvars]
+void refshim_basis_at(void *hh, int npts, const double *Z, double *out){
+  RefHandle *h = (RefHandle*)hh;
+  int N = h->pc->getNumBasisTerms(), nv = h->nvars;
+  scalar *z = (scalar*)Z, *o = (scalar*)out;
+  for (int k = 0; k < N; k++)
+    for (int p = 0; p < npts; p++) o[(size_t)k*npts + p] = h->pc->basis(k, z + (size_t)p*nv);
+}
+
+// 1-D rule / polynomial of one parameter of the container
+void refshim_param_quadrature(void *hh, int pid, int npoints, double *z, double *y, double *w){
+  ((RefHandle*)hh)->params[pid]->quadrature(npoints, (scalar*)z, (scalar*)y, (scalar*)w);
+}
+void refshim_param_basis(void *hh, int pid, int npts, const double *z, int d, double *out){
+  RefHandle *h = (RefHandle*)hh;
+  for (int p = 0; p < npts; p++) ((scalar*)out)[p] = h->params[pid]->basis(((const scalar*)z)[p], d);
+}
+
+// F[k][c] = sum_q (basis(k,zq)*wq) * f[q][c]      k in [k0,k1)   (TACSStochasticElement.cpp:283-311)
+void refshim_project_vector(void *hh, int m, const double *f_, int k0, int k1, double *F_){
+  RefHandle *h = (RefHandle*)hh;
+  const scalar *f = (const scalar*)f_; scalar *F = (scalar*)F_;
+  int Q = h->pc->getNumQuadraturePoints(), nv = h->nvars;
+  std::vector<scalar> zq(nv), yq(nv);
+  for (int i = k0; i < k1; i++){
+    scalar *r = F + (size_t)(i-k0)*m;
+    for (int c = 0; c < m; c++) r[c] = 0.0;
+    for (int q = 0; q < Q; q++){
+      scalar wq = h->pc->quadrature(q, zq.data(), yq.data());
+      scalar scale = h->pc->basis(i, zq.data())*wq;
+      const scalar *fq = f + (size_t)q*m;
+      for (int c = 0; c < m; c++) r[c] += fq[c]*scale;
+    }
+  }
+}
+
+// C[(i-i0)][(j-j0)][c] = sum_q (basis(i,zq)*basis(j,zq)*wq) * J[q][c]   (TACSStochasticElement.cpp:380-414)
+// rows i are partitioned over nthreads std::threads (container reads are thread-safe after initialize()).
+static void matrix_rows(RefHandle *h, int m2, const scalar *J, int ia, int ib, int i0, int j0, int j1, scalar *C){
+  int Q = h->pc->getNumQuadraturePoints(), nv = h->nvars;
+  std::vector<scalar> zq(nv), yq(nv);
+  int nj = j1 - j0;
+  for (int i = ia; i < ib; i++){
+    for (int j = j0; j < j1; j++){
+      scalar *A = C + ((size_t)(i-i0)*nj + (j-j0))*m2;
+      for (int c = 0; c < m2; c++) A[c] = 0.0;
+      for (int q = 0; q < Q; q++){
+        scalar wq = h->pc->quadrature(q, zq.data(), yq.data());
+        scalar scale = h->pc->basis(i, zq.data())*h->pc->basis(j, zq.data())*wq;
+        const scalar *Jq = J + (size_t)q*m2;
+        for (int c = 0; c < m2; c++) A[c] += scale*Jq[c];
+      }
+    }
+  }
+}
+void refshim_project_matrix(void *hh, int m2, const double *J_, int i0, int i1, int j0, int j1,
+                            double *C_, int nthreads){
+  RefHandle *h = (RefHandle*)hh;
+  const scalar *J = (const scalar*)J_; scalar *C = (scalar*)C_;
+  if (nthreads <= 1){ matrix_rows(h, m2, J, i0, i1, i0, j0, j1, C); return; }
+  std::vector<std::thread> th;
+  int rows = i1 - i0;
+  for (int t = 0; t < nthreads; t++){
+    int ia = i0 + (int)((long long)rows*t/nthreads), ib = i0 + (int)((long long)rows*(t+1)/nthreads);
+    if (ib > ia) th.emplace_back(matrix_rows, h, m2, J, ia, ib, i0, j0, j1, C);
+  }
+  for (auto &t : th) t.join();
+}
+
+} // extern "C"
