@@ -1,0 +1,149 @@
+/* pspace_cuda.h — C-ABI of the B200-native stochastic-Galerkin projection path (libpspace_cuda.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, `extern "C"`, int status returns, no C++ or
+ * torch types.  The host C++ library (libpspace.so: ParameterFactory / ParameterContainer with the
+ * reference's own headers and signatures) calls ONLY these entry points for everything batched; a
+ * maintainer of the reference binds them the same way.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference root).
+ *
+ * Scalars: `double` in the real build; in the USE_COMPLEX build (reference src/include/scalar.h:18-24)
+ * a scalar is an interleaved (re,im) pair of doubles.  A context is created real or complex
+ * (`is_complex`), and every `scalar` array argument below is `const double*` / `double*` holding
+ * 1 or 2 doubles per scalar accordingly.
+ *
+ * Memory: arguments named d_* are DEVICE pointers owned by the caller; h_* are HOST pointers.
+ * Streams: `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ * Errors: every function returns PSPACE_OK (0) or a negative PSPACE_E* code; pspace_cuda_last_error()
+ * returns a thread-local message.  There is NO CPU fallback: without a usable CUDA device the calls
+ * fail with PSPACE_ECUDA.
+ */
+#ifndef PSPACE_CUDA_H
+#define PSPACE_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSPACE_OK 0
+#define PSPACE_EINVAL (-1)   /* bad argument */
+#define PSPACE_ECUDA (-2)    /* CUDA runtime error (message has the cudaError string) */
+#define PSPACE_ESTATE (-3)   /* call out of order (e.g. project before initialize) */
+#define PSPACE_ENOMEM (-4)
+#define PSPACE_MAX_VARS 32
+#define PSPACE_MAX_NQ 20     /* 1-D rules exist for npoints 1..20 (GaussianQuadrature.cpp:31-1483) */
+
+/* parameter kinds = the three ParameterFactory products (src/include/ParameterFactory.h:21-28) */
+#define PSPACE_NORMAL 0       /* (mu, sigma)  Gauss-Hermite / unit Hermite  */
+#define PSPACE_UNIFORM 1      /* (a, b)       Gauss-Legendre / unit shifted Legendre */
+#define PSPACE_EXPONENTIAL 2  /* (mu, beta)   Gauss-Laguerre / Laguerre */
+
+typedef struct pspace_ctx pspace_ctx;
+
+const char *pspace_cuda_last_error(void);
+int pspace_cuda_version(void);
+/* number of visible CUDA devices, or a negative error code */
+int pspace_cuda_device_count(void);
+
+/* ---- context = device-side state of one ParameterContainer (src/include/ParameterContainer.h:17-58) --
+ * kinds[nvars], p1/p2[nvars] scalars (host), dmax[nvars]; basis_type 0 tensor / !=0 complete
+ * (BasisHelper.cpp:40-61).  Replaces: ParameterContainer ctor + addParameter (ParameterContainer.cpp:11-15,50-56). */
+int pspace_cuda_create(pspace_ctx **out, int device, int is_complex, int nvars, const int *kinds,
+                       const double *h_p1, const double *h_p2, const int *dmax, int basis_type);
+int pspace_cuda_destroy(pspace_ctx *ctx);
+
+/* ---- (1) multi-index basis construction: integer kernel, bit-exact ------------------------------
+ * Replaces BasisHelper::basisDegrees (BasisHelper.cpp:33-66 and the unrolled variants :98-584) as
+ * called by ParameterContainer::initializeBasis (ParameterContainer.cpp:84-109).
+ * Stateless form: writes d_out[nbasis][nvars] (capacity_rows rows available) and *nbasis.  */
+int pspace_cuda_basis_degrees(int nvars, const int *pmax, int basis_type, int *nbasis, int *d_out,
+                              long long capacity_rows, void *stream);
+/* number of basis terms without producing them (for sizing d_out) */
+int pspace_cuda_basis_count(int nvars, const int *pmax, int basis_type, long long *nbasis);
+/* context form: builds and keeps the degree table on the device */
+int pspace_cuda_initialize_basis(pspace_ctx *ctx, const int *pmax, void *stream);
+
+/* ---- (2) 1-D rules, orthonormal 1-D basis tables, tensor grid ------------------------------------
+ * Replaces ParameterContainer::initializeQuadrature (ParameterContainer.cpp:116-160):
+ * {Normal,Uniform,Exponential}Parameter::quadrature -> GaussianQuadrature::*Quadrature
+ * (GaussianQuadrature.cpp:510-514,1026-1032,1479-1482), QuadratureHelper::tensorProduct
+ * (QuadratureHelper.cpp:34-132), and tabulates unit_{hermite,legendre,laguerre}
+ * (OrthogonalPolynomials.cpp:42-44,66-68,90-92) at the 1-D nodes. */
+int pspace_cuda_initialize_quadrature(pspace_ctx *ctx, const int *nqpts, void *stream);
+/* ParameterContainer::initialize (ParameterContainer.cpp:224-237): pmax = dmax, nq = dmax+1 */
+int pspace_cuda_initialize(pspace_ctx *ctx, void *stream);
+
+/* accessors (ParameterContainer.cpp:61-77) */
+int pspace_cuda_num_basis(const pspace_ctx *ctx);
+int pspace_cuda_num_params(const pspace_ctx *ctx);
+long long pspace_cuda_num_quad(const pspace_ctx *ctx);
+int pspace_cuda_is_complex(const pspace_ctx *ctx);
+/* copy results back to the host (the host library mirrors them for the per-call accessors
+ * getBasisParamDeg / quadrature(q,zq,yq), ParameterContainer.cpp:169-176,200-205) */
+int pspace_cuda_get_degrees(const pspace_ctx *ctx, int *h_out /*[N][nvars]*/);
+int pspace_cuda_get_rules(const pspace_ctx *ctx, int pid, double *h_z, double *h_y, double *h_w /*[nq_pid] scalars*/);
+int pspace_cuda_get_table(const pspace_ctx *ctx, int pid, double *h_T /*[(pmax+1)][nq] scalars*/);
+int pspace_cuda_get_weights(const pspace_ctx *ctx, long long q0, long long q1, double *h_W /*[q1-q0] scalars*/);
+/* materialise grid columns q0..q1-1: d_Z,d_Y [q1-q0][nvars] scalars (point-major), d_W [q1-q0]; any may be NULL
+ * (QuadratureHelper.cpp:105-129; layout as handed out by quadrature(q,zq,yq)) */
+int pspace_cuda_tensor_grid(const pspace_ctx *ctx, long long q0, long long q1, double *d_Z, double *d_Y,
+                            double *d_W, void *stream);
+
+/* ---- (2b) batched basis evaluation ---------------------------------------------------------------
+ * Replaces N*npts calls of ParameterContainer::basis(k, z) (ParameterContainer.cpp:184-192).
+ * Grid form: d_psi[(k1-k0)][(q1-q0)] = psi_k(z_q) at quadrature points (table products).
+ * Point form: arbitrary points d_z[npts][nvars]; polynomials evaluated with the reference formulas. */
+int pspace_cuda_eval_basis_grid(const pspace_ctx *ctx, int k0, int k1, long long q0, long long q1,
+                                double *d_psi, void *stream);
+int pspace_cuda_eval_basis_points(const pspace_ctx *ctx, int k0, int k1, long long npts, const double *d_z,
+                                  double *d_psi, void *stream);
+
+/* ---- (3) Galerkin projections ---------------------------------------------------------------------
+ * Vector: F[k][c] = sum_q w_q psi_k(z_q) f[q][c]        (TACSStochasticElement.cpp:283-311 addResidual,
+ *         :196-238 getInitConditions, :487-530 evalPointQuantity; pspace/core.py:750-818)
+ * Matrix: C[i][j][c] = sum_q w_q psi_i(z_q) psi_j(z_q) J[q][c]   (TACSStochasticElement.cpp:380-414
+ *         addJacobian; pspace/core.py:840-911), all ordered pairs of the window [i0,i1) x [j0,j1).
+ * q runs over [q0,q1) (a quadrature-point shard; the full projection is q0=0,q1=Q); d_f / d_J hold ONLY
+ * rows q0..q1-1: d_f[(q1-q0)][ncols], d_J[(q1-q0)][ncols] scalars, row-major, ncols = m resp. m*m.
+ * Output: d_F[(k1-k0)][ncols]; d_C[(i1-i0)][(j1-j0)][ncols] scalars, row-major.
+ * accumulate = 0 overwrites the output, 1 adds to it (the reference callers add into res/mat).
+ * Workspace: the call may need scratch for its split over q; query with *_workspace and pass a device
+ * buffer of at least that many bytes (may be NULL when the query returns 0). */
+typedef struct {
+  int k0, k1;               /* vector: basis range; matrix: i range */
+  int j0, j1;               /* matrix only: j range */
+  long long q0, q1;         /* quadrature-point range of this call */
+  int ncols;                /* m (vector) or m*m (matrix), in scalars */
+  int accumulate;
+  int ksplit;               /* 0 = let the library choose; >0 forces the number of q-slices */
+  int variant;              /* 0 = auto; otherwise a tile-variant id (bench / tuning) */
+} pspace_project_args;
+
+size_t pspace_cuda_project_workspace(const pspace_ctx *ctx, int is_matrix, const pspace_project_args *a);
+int pspace_cuda_project_vector(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_f,
+                               double *d_F, void *d_workspace, size_t workspace_bytes, void *stream);
+int pspace_cuda_project_matrix(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_J,
+                               double *d_C, void *d_workspace, size_t workspace_bytes, void *stream);
+/* Host-buffer forms (the call a host-side user of the reference makes: pageable or pinned host
+ * arrays in, host array out; H2D + kernels + D2H inside, synchronous). */
+int pspace_cuda_project_vector_host(pspace_ctx *ctx, const pspace_project_args *a, const double *h_f, double *h_F);
+int pspace_cuda_project_matrix_host(pspace_ctx *ctx, const pspace_project_args *a, const double *h_J, double *h_C);
+
+/* launches of this library's kernels since the context was created (bench "gpu_launches") */
+long long pspace_cuda_launch_count(const pspace_ctx *ctx);
+/* description + FLOP count of the kernel the last project call used */
+int pspace_cuda_last_plan(const pspace_ctx *ctx, char *buf, int buflen);
+
+/* ---- measurement helpers (bench.py) --------------------------------------------------------------
+ * FP64 peak of this device measured with a register-resident loop: mode 0 = DFMA pipe,
+ * 1 = DMMA (mma.sync.m8n8k4.f64).  Runs ~ms_target milliseconds; returns TFLOP/s. */
+int pspace_cuda_fp64_peak(int device, int mode, double ms_target, double *tflops);
+/* splitmix64 synthetic blocks written on the device: out[i] = u(seed ^ (offset+i)) in (-0.5,0.5) */
+int pspace_cuda_fill_synthetic(double *d_out, long long n, unsigned long long seed, unsigned long long offset,
+                               void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,271 @@
+// C-ABI layer (include/pspace_cuda.h): context management, argument checking, error reporting and the
+// host-buffer entry points.  All numerics live in basis.cu / tables.cu / project.cu.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include "ctx.h"
+
+static thread_local char g_err[512] = "";
+
+int ps_fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+extern "C" {
+
+const char *pspace_cuda_last_error(void) { return g_err; }
+int pspace_cuda_version(void) { return 100; }
+
+int pspace_cuda_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return ps_fail(PSPACE_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  return n;
+}
+
+int pspace_cuda_create(pspace_ctx **out, int device, int is_complex, int nvars, const int *kinds, const double *h_p1,
+                       const double *h_p2, const int *dmax, int basis_type) {
+  if (!out || !kinds || !h_p1 || !h_p2 || !dmax) return ps_fail(PSPACE_EINVAL, "null argument");
+  if (nvars < 1 || nvars > PSPACE_MAX_VARS) return ps_fail(PSPACE_EINVAL, "nvars %d outside 1..%d", nvars, PSPACE_MAX_VARS);
+  int ndev = pspace_cuda_device_count();
+  if (ndev < 0) return ndev;
+  if (ndev == 0) return ps_fail(PSPACE_ECUDA, "no CUDA device: the pspace GPU path has no CPU fallback");
+  if (device < 0 || device >= ndev) return ps_fail(PSPACE_EINVAL, "device %d outside 0..%d", device, ndev - 1);
+  PS_CUDA(cudaSetDevice(device));
+  pspace_ctx *c = new pspace_ctx();
+  c->device = device;
+  c->is_complex = is_complex ? 1 : 0;
+  c->width = is_complex ? 2 : 1;
+  c->nvars = nvars;
+  c->basis_type = basis_type;
+  for (int d = 0; d < nvars; d++) {
+    if (kinds[d] < 0 || kinds[d] > 2) { delete c; return ps_fail(PSPACE_EINVAL, "kinds[%d]=%d", d, kinds[d]); }
+    c->kinds[d] = kinds[d];
+    c->dmax[d] = dmax[d];
+    for (int w = 0; w < c->width; w++) {
+      c->p1[c->width * d + w] = h_p1[c->width * d + w];
+      c->p2[c->width * d + w] = h_p2[c->width * d + w];
+    }
+  }
+  *out = c;
+  return PSPACE_OK;
+}
+
+int pspace_cuda_destroy(pspace_ctx *c) {
+  if (!c) return PSPACE_OK;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_deg); cudaFree(c->d_zp); cudaFree(c->d_yp); cudaFree(c->d_wp); cudaFree(c->d_T);
+  cudaFree(c->d_qdig); cudaFree(c->d_W);
+  cudaFree(c->d_scratch_in); cudaFree(c->d_scratch_out); cudaFree(c->d_scratch_ws);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return PSPACE_OK;
+}
+
+int pspace_cuda_basis_count(int nvars, const int *pmax, int basis_type, long long *nbasis) {
+  if (!pmax || !nbasis) return ps_fail(PSPACE_EINVAL, "null argument");
+  return ps_basis_count_host(nvars, pmax, basis_type, nbasis);
+}
+
+int pspace_cuda_basis_degrees(int nvars, const int *pmax, int basis_type, int *nbasis, int *d_out, long long capacity_rows,
+                              void *stream) {
+  if (!pmax || !nbasis || !d_out) return ps_fail(PSPACE_EINVAL, "null argument");
+  return ps_basis_degrees_device(nvars, pmax, basis_type, nbasis, d_out, capacity_rows, (cudaStream_t)stream, nullptr);
+}
+
+int pspace_cuda_initialize_basis(pspace_ctx *c, const int *pmax, void *stream) {
+  if (!c || !pmax) return ps_fail(PSPACE_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  PS_CUDA(cudaSetDevice(c->device));
+  long long n = 0;
+  int rc = ps_basis_count_host(c->nvars, pmax, c->basis_type, &n);
+  if (rc) return rc;
+  if (n > 0x7fffffffLL / c->nvars) return ps_fail(PSPACE_EINVAL, "basis of %lld terms is too large", n);
+  if (c->d_deg) { PS_CUDA(cudaFree(c->d_deg)); c->d_deg = nullptr; }
+  PS_CUDA(cudaMalloc(&c->d_deg, sizeof(int) * (size_t)n * c->nvars));
+  int nb = 0;
+  rc = ps_basis_degrees_device(c->nvars, pmax, c->basis_type, &nb, c->d_deg, n, st, &c->launches);
+  if (rc) return rc;
+  if (nb != n) return ps_fail(PSPACE_ECUDA, "internal: device produced %d basis terms, expected %lld", nb, n);
+  c->N = nb;
+  for (int d = 0; d < c->nvars; d++) c->pmax[d] = pmax[d];
+  c->h_deg.resize((size_t)nb * c->nvars);
+  PS_CUDA(cudaMemcpyAsync(c->h_deg.data(), c->d_deg, sizeof(int) * c->h_deg.size(), cudaMemcpyDeviceToHost, st));
+  PS_CUDA(cudaStreamSynchronize(st));
+  c->basis_ready = true;
+  return ps_build_tables(c, st);
+}
+
+int pspace_cuda_initialize_quadrature(pspace_ctx *c, const int *nqpts, void *stream) {
+  if (!c || !nqpts) return ps_fail(PSPACE_EINVAL, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  PS_CUDA(cudaSetDevice(c->device));
+  long long Q = 1;
+  for (int d = 0; d < c->nvars; d++) {
+    if (nqpts[d] < 1 || nqpts[d] > PSPACE_MAX_NQ) return ps_fail(PSPACE_EINVAL, "nqpts[%d]=%d outside 1..%d", d, nqpts[d], PSPACE_MAX_NQ);
+    if (Q > (1LL << 40) / nqpts[d]) return ps_fail(PSPACE_EINVAL, "quadrature grid exceeds 2^40 points");
+    Q *= nqpts[d];
+  }
+  for (int d = 0; d < c->nvars; d++) c->nq[d] = nqpts[d];
+  c->Q = Q;
+  c->quad_ready = true;
+  int rc = ps_build_tables(c, st);
+  if (rc) return rc;
+  rc = ps_build_grid(c, st);
+  if (rc) return rc;
+  PS_CUDA(cudaStreamSynchronize(st));
+  return PSPACE_OK;
+}
+
+int pspace_cuda_initialize(pspace_ctx *c, void *stream) {
+  if (!c) return ps_fail(PSPACE_EINVAL, "null argument");
+  int pm[PSPACE_MAX_VARS], nq[PSPACE_MAX_VARS];
+  for (int d = 0; d < c->nvars; d++) { pm[d] = c->dmax[d]; nq[d] = c->dmax[d] + 1; }
+  int rc = pspace_cuda_initialize_basis(c, pm, stream);
+  if (rc) return rc;
+  return pspace_cuda_initialize_quadrature(c, nq, stream);
+}
+
+int pspace_cuda_num_basis(const pspace_ctx *c) { return c ? c->N : 0; }
+int pspace_cuda_num_params(const pspace_ctx *c) { return c ? c->nvars : 0; }
+long long pspace_cuda_num_quad(const pspace_ctx *c) { return c ? c->Q : 0; }
+int pspace_cuda_is_complex(const pspace_ctx *c) { return c ? c->is_complex : 0; }
+
+int pspace_cuda_get_degrees(const pspace_ctx *c, int *h_out) {
+  if (!c || !h_out) return ps_fail(PSPACE_EINVAL, "null argument");
+  if (!c->basis_ready) return ps_fail(PSPACE_ESTATE, "basis not initialised");
+  memcpy(h_out, c->h_deg.data(), sizeof(int) * c->h_deg.size());
+  return PSPACE_OK;
+}
+
+int pspace_cuda_get_rules(const pspace_ctx *c, int pid, double *h_z, double *h_y, double *h_w) {
+  if (!c) return ps_fail(PSPACE_EINVAL, "null argument");
+  if (!c->quad_ready) return ps_fail(PSPACE_ESTATE, "quadrature not initialised");
+  if (pid < 0 || pid >= c->nvars) return ps_fail(PSPACE_EINVAL, "parameter id %d", pid);
+  PS_CUDA(cudaSetDevice(c->device));
+  size_t off = (size_t)c->roff[pid] * c->width, bytes = sizeof(double) * c->width * c->nq[pid];
+  if (h_z) PS_CUDA(cudaMemcpy(h_z, c->d_zp + off, bytes, cudaMemcpyDeviceToHost));
+  if (h_y) PS_CUDA(cudaMemcpy(h_y, c->d_yp + off, bytes, cudaMemcpyDeviceToHost));
+  if (h_w) PS_CUDA(cudaMemcpy(h_w, c->d_wp + off, bytes, cudaMemcpyDeviceToHost));
+  return PSPACE_OK;
+}
+
+int pspace_cuda_get_table(const pspace_ctx *c, int pid, double *h_T) {
+  if (!c || !h_T) return ps_fail(PSPACE_EINVAL, "null argument");
+  if (!c->tables_ready) return ps_fail(PSPACE_ESTATE, "tables need both basis and quadrature");
+  if (pid < 0 || pid >= c->nvars) return ps_fail(PSPACE_EINVAL, "parameter id %d", pid);
+  PS_CUDA(cudaSetDevice(c->device));
+  PS_CUDA(cudaMemcpy(h_T, c->d_T + (size_t)c->toff[pid] * c->width,
+                     sizeof(double) * c->width * (c->pmax[pid] + 1) * c->nq[pid], cudaMemcpyDeviceToHost));
+  return PSPACE_OK;
+}
+
+int pspace_cuda_get_weights(const pspace_ctx *c, long long q0, long long q1, double *h_W) {
+  if (!c || !h_W) return ps_fail(PSPACE_EINVAL, "null argument");
+  if (!c->quad_ready) return ps_fail(PSPACE_ESTATE, "quadrature not initialised");
+  if (q0 < 0 || q1 > c->Q || q1 < q0) return ps_fail(PSPACE_EINVAL, "q range");
+  PS_CUDA(cudaSetDevice(c->device));
+  PS_CUDA(cudaMemcpy(h_W, c->d_W + (size_t)q0 * c->width, sizeof(double) * c->width * (size_t)(q1 - q0), cudaMemcpyDeviceToHost));
+  return PSPACE_OK;
+}
+
+int pspace_cuda_tensor_grid(const pspace_ctx *c, long long q0, long long q1, double *d_Z, double *d_Y, double *d_W,
+                            void *stream) {
+  if (!c) return ps_fail(PSPACE_EINVAL, "null argument");
+  if (!c->quad_ready) return ps_fail(PSPACE_ESTATE, "quadrature not initialised");
+  if (q0 < 0 || q1 > c->Q || q1 < q0) return ps_fail(PSPACE_EINVAL, "q range");
+  PS_CUDA(cudaSetDevice(c->device));
+  return ps_tensor_grid(c, q0, q1, d_Z, d_Y, d_W, (cudaStream_t)stream);
+}
+
+int pspace_cuda_eval_basis_grid(const pspace_ctx *c, int k0, int k1, long long q0, long long q1, double *d_psi, void *stream) {
+  if (!c || !d_psi) return ps_fail(PSPACE_EINVAL, "null argument");
+  if (!c->tables_ready) return ps_fail(PSPACE_ESTATE, "eval_basis needs basis and quadrature");
+  if (k0 < 0 || k1 > c->N || k1 < k0 || q0 < 0 || q1 > c->Q || q1 < q0) return ps_fail(PSPACE_EINVAL, "range");
+  PS_CUDA(cudaSetDevice(c->device));
+  return ps_eval_basis_grid(c, k0, k1, q0, q1, d_psi, (cudaStream_t)stream);
+}
+
+int pspace_cuda_eval_basis_points(const pspace_ctx *c, int k0, int k1, long long npts, const double *d_z, double *d_psi,
+                                  void *stream) {
+  if (!c || !d_psi || !d_z) return ps_fail(PSPACE_EINVAL, "null argument");
+  if (!c->basis_ready) return ps_fail(PSPACE_ESTATE, "basis not initialised");
+  if (k0 < 0 || k1 > c->N || k1 < k0 || npts < 0) return ps_fail(PSPACE_EINVAL, "range");
+  PS_CUDA(cudaSetDevice(c->device));
+  return ps_eval_basis_points(c, k0, k1, npts, d_z, d_psi, (cudaStream_t)stream);
+}
+
+size_t pspace_cuda_project_workspace(const pspace_ctx *c, int is_matrix, const pspace_project_args *a) {
+  if (!c || !a) return 0;
+  return ps_project_workspace(c, is_matrix, a);
+}
+
+int pspace_cuda_project_vector(const pspace_ctx *c, const pspace_project_args *a, const double *d_f, double *d_F,
+                               void *d_ws, size_t ws_bytes, void *stream) {
+  if (!c || !a) return ps_fail(PSPACE_EINVAL, "null argument");
+  if ((!d_f && a->q1 > a->q0) || (!d_F && a->k1 > a->k0)) return ps_fail(PSPACE_EINVAL, "null buffer for a non-empty range");
+  PS_CUDA(cudaSetDevice(c->device));
+  return ps_project(c, 0, a, d_f, d_F, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int pspace_cuda_project_matrix(const pspace_ctx *c, const pspace_project_args *a, const double *d_J, double *d_C,
+                               void *d_ws, size_t ws_bytes, void *stream) {
+  if (!c || !a) return ps_fail(PSPACE_EINVAL, "null argument");
+  if ((!d_J && a->q1 > a->q0) || (!d_C && a->k1 > a->k0 && a->j1 > a->j0))
+    return ps_fail(PSPACE_EINVAL, "null buffer for a non-empty range");
+  PS_CUDA(cudaSetDevice(c->device));
+  return ps_project(c, 1, a, d_J, d_C, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+static int ensure(void **buf, size_t *have, size_t need) {
+  if (need <= *have) return PSPACE_OK;
+  if (*buf) { PS_CUDA(cudaFree(*buf)); *buf = nullptr; *have = 0; }
+  if (need) PS_CUDA(cudaMalloc(buf, need));
+  *have = need;
+  return PSPACE_OK;
+}
+
+static int project_host(pspace_ctx *c, int is_matrix, const pspace_project_args *a, const double *h_in, double *h_out) {
+  if (!c || !a || !h_in || !h_out) return ps_fail(PSPACE_EINVAL, "null argument");
+  PS_CUDA(cudaSetDevice(c->device));
+  if (!c->own_stream) PS_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  cudaStream_t st = c->own_stream;
+  const size_t w = c->width;
+  if (a->q1 < a->q0 || a->k1 < a->k0 || (is_matrix && a->j1 < a->j0)) return ps_fail(PSPACE_EINVAL, "range");
+  const size_t in_bytes = sizeof(double) * w * (size_t)(a->q1 - a->q0) * a->ncols;
+  const size_t rows = is_matrix ? (size_t)(a->k1 - a->k0) * (a->j1 - a->j0) : (size_t)(a->k1 - a->k0);
+  const size_t out_bytes = sizeof(double) * w * rows * a->ncols;
+  const size_t ws = ps_project_workspace(c, is_matrix, a);
+  int rc;
+  if ((rc = ensure(&c->d_scratch_in, &c->scratch_in_bytes, in_bytes))) return rc;
+  if ((rc = ensure(&c->d_scratch_out, &c->scratch_out_bytes, out_bytes))) return rc;
+  if ((rc = ensure(&c->d_scratch_ws, &c->scratch_ws_bytes, ws))) return rc;
+  PS_CUDA(cudaMemcpyAsync(c->d_scratch_in, h_in, in_bytes, cudaMemcpyHostToDevice, st));
+  if (a->accumulate) PS_CUDA(cudaMemcpyAsync(c->d_scratch_out, h_out, out_bytes, cudaMemcpyHostToDevice, st));
+  rc = ps_project(c, is_matrix, a, (const double *)c->d_scratch_in, (double *)c->d_scratch_out, c->d_scratch_ws, ws, st);
+  if (rc) return rc;
+  PS_CUDA(cudaMemcpyAsync(h_out, c->d_scratch_out, out_bytes, cudaMemcpyDeviceToHost, st));
+  PS_CUDA(cudaStreamSynchronize(st));
+  return PSPACE_OK;
+}
+
+int pspace_cuda_project_vector_host(pspace_ctx *c, const pspace_project_args *a, const double *h_f, double *h_F) {
+  return project_host(c, 0, a, h_f, h_F);
+}
+int pspace_cuda_project_matrix_host(pspace_ctx *c, const pspace_project_args *a, const double *h_J, double *h_C) {
+  return project_host(c, 1, a, h_J, h_C);
+}
+
+long long pspace_cuda_launch_count(const pspace_ctx *c) { return c ? c->launches : 0; }
+
+int pspace_cuda_last_plan(const pspace_ctx *c, char *buf, int buflen) {
+  if (!c || !buf || buflen < 1) return ps_fail(PSPACE_EINVAL, "null argument");
+  snprintf(buf, buflen, "%s flop=%.6e", c->plan.c_str(), c->plan_flop);
+  return PSPACE_OK;
+}
+
+}  // extern "C"

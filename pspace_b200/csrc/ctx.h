@@ -1,0 +1,63 @@
+// Internal: device-side state of one ParameterContainer (behind the opaque pspace_ctx of include/pspace_cuda.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/pspace_cuda.h"
+
+struct pspace_ctx {
+  int device = 0, is_complex = 0, nvars = 0, basis_type = 0, width = 1;  // width = doubles per scalar
+  int kinds[PSPACE_MAX_VARS] = {0}, dmax[PSPACE_MAX_VARS] = {0};
+  double p1[2 * PSPACE_MAX_VARS] = {0}, p2[2 * PSPACE_MAX_VARS] = {0};
+  bool basis_ready = false, quad_ready = false, tables_ready = false;
+  int pmax[PSPACE_MAX_VARS] = {0}, nq[PSPACE_MAX_VARS] = {0};
+  int N = 0;
+  long long Q = 0;
+  int *d_deg = nullptr;                  // [N][nvars]
+  std::vector<int> h_deg;
+  int roff[PSPACE_MAX_VARS + 1] = {0};   // rule offsets (scalars): rule of parameter d at roff[d], nq[d] entries
+  double *d_zp = nullptr, *d_yp = nullptr, *d_wp = nullptr;
+  int toff[PSPACE_MAX_VARS + 1] = {0};   // table offsets (scalars): T_d at toff[d], (pmax[d]+1) x nq[d], row-major
+  int tsz = 0;
+  double *d_T = nullptr;
+  int DP = 16;                           // bytes per row of the digit table (16 or 32)
+  uint8_t *d_qdig = nullptr;             // [Q][DP] mixed-radix digits of q (last variable fastest)
+  double *d_W = nullptr;                 // [Q] scalars
+  long long launches = 0;
+  std::string plan;
+  double plan_flop = 0.0;
+  // scratch owned by the context for the host-buffer entry points
+  void *d_scratch_in = nullptr, *d_scratch_out = nullptr, *d_scratch_ws = nullptr;
+  size_t scratch_in_bytes = 0, scratch_out_bytes = 0, scratch_ws_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+};
+
+// error plumbing (capi.cu)
+int ps_fail(int code, const char *fmt, ...);
+#define PS_CUDA(call)                                                                        \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return ps_fail(PSPACE_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define PS_LAUNCH_CHECK(ctxp)                                                                \
+  do {                                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                                    \
+    if (e__ != cudaSuccess)                                                                  \
+      return ps_fail(PSPACE_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+    if (ctxp) ((pspace_ctx *)(ctxp))->launches++;                                            \
+  } while (0)
+
+// implemented in basis.cu / tables.cu / project.cu, called from capi.cu
+int ps_basis_degrees_device(int nvars, const int *pmax, int basis_type, int *nbasis, int *d_out,
+                            long long capacity_rows, cudaStream_t st, long long *launches);
+int ps_basis_count_host(int nvars, const int *pmax, int basis_type, long long *nbasis);
+int ps_build_tables(pspace_ctx *ctx, cudaStream_t st);
+int ps_build_grid(pspace_ctx *ctx, cudaStream_t st);
+int ps_tensor_grid(const pspace_ctx *ctx, long long q0, long long q1, double *d_Z, double *d_Y, double *d_W, cudaStream_t st);
+int ps_eval_basis_grid(const pspace_ctx *ctx, int k0, int k1, long long q0, long long q1, double *d_psi, cudaStream_t st);
+int ps_eval_basis_points(const pspace_ctx *ctx, int k0, int k1, long long npts, const double *d_z, double *d_psi, cudaStream_t st);
+size_t ps_project_workspace(const pspace_ctx *ctx, int is_matrix, const pspace_project_args *a);
+int ps_project(const pspace_ctx *ctx, int is_matrix, const pspace_project_args *a, const double *d_in, double *d_out,
+               void *d_ws, size_t ws_bytes, cudaStream_t st);

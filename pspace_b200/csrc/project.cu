@@ -1,0 +1,534 @@
+// (3) Galerkin projection — the hot path.
+//
+//   matrix:  C[i][j][c] = sum_q (w_q psi_i(z_q) psi_j(z_q)) J[q][c]      TACSStochasticElement.cpp:380-414
+//   vector:  F[k][c]    = sum_q (w_q psi_k(z_q)) f[q][c]                 TACSStochasticElement.cpp:283-311
+//
+// i.e. the dense contraction (N^2 x Q).(Q x m^2) with a GENERATED left operand.  The reference evaluates
+// it as N^2*Q scalar calls of basis()/quadrature(); here it is one FP64 tensor-core GEMM:
+//
+//  * math: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  Measured on this B200 (profiles/r01_fp64_peak.md):
+//    DMMA sustains 37.0 TFLOP/s = 99.5 % of 148 SM x 64 FMA/clk x 1.965 GHz, the DFMA pipe 33.5 — both
+//    issue to the same FP64 pipe (mixing them adds nothing), DMMA needs 1/8 of the issue slots and no
+//    per-FMA operand fetch, so DMMA it is.  tcgen05 has no FP64 kind.
+//  * right operand J[q][c]: streamed from HBM/L2 once per CTA tile with 16-byte cp.async (LDGSTS) into a
+//    STAGES-deep shared-memory ring, row pitch BN+4 doubles so the DMMA B-fragment reads
+//    (k = lane%4, n = lane/4) hit 16 distinct banks.
+//  * left operand: never materialised.  A CTA tile is BI basis rows i x 8 basis rows j (= BM = 8*BI
+//    ordered pairs); per chunk of KQ=32 quadrature points the CTA stages psi_i(z_q) (BI x KQ) and
+//    w_q psi_j(z_q) (8 x KQ) in shared memory as products of the 1-D tables T_d[alpha][i_d] (also in
+//    shared memory) selected by the mixed-radix digits of q, in the reference's product order
+//    (ParameterContainer.cpp:184-192).  Each lane then forms its A-fragment element
+//    a[row=(i,j)][k=q] = psi_i(q) * (w_q psi_j(q)) with ONE DMUL that feeds WN DMMAs.
+//  * USE_COMPLEX: J, psi and C are interleaved (re,im); C = A_re*[B] + A_im*[B'] with
+//    B'[k][2c] = -B[k][2c+1], B'[k][2c+1] = B[k][2c]  (4 real FMAs per complex FMA, naive complex multiply
+//    so complex-step imaginary parts survive).
+//  * q-range [q0,q1) is a call argument (multi-GPU shard) and is further cut into `ksplit` slices over
+//    blockIdx.y; slices write partial tiles to a workspace that a second kernel sums in slice order
+//    (deterministic — no atomics).
+#include "ctx.h"
+#include <algorithm>
+#include <stdio.h>
+
+namespace {
+
+constexpr int NT = 256;   // 8 warps
+constexpr int KQ = 32;    // quadrature points per pipeline stage (8 DMMA k-steps)
+constexpr int ZPAD = PSPACE_MAX_NQ;   // zero scalars appended to the staged tables (target of invalid rows)
+
+enum { MODE_MATRIX = 0, MODE_VECTOR = 1 };
+
+struct ProjParams {
+  const double *in;        // J or f rows q0..q1-1, pitch ld_in doubles
+  long long ld_in;
+  double *out;             // C window / F rows, or the split workspace
+  long long stride_i, stride_j, slice_stride;   // in doubles
+  int i0, ni, j0, nj;      // matrix: window; vector: j0/nj = basis range, ni = 1
+  long long q0, q1;
+  int ncols_d;             // real columns (= ncols * width)
+  int nvars, tsz, DP;
+  const double *T;
+  const int *deg;
+  const uint8_t *qdig;
+  const double *W;
+  int toff[PSPACE_MAX_VARS], nq[PSPACE_MAX_VARS];
+  int tiles_n, tiles_j, tiles_i;
+  long long chunks_per_slice;
+  int accumulate, vec16;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gptr, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gptr), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gptr, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gptr), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double flip_sign(double x, unsigned mask) {   // x * (+-1) on the integer pipe
+  return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
+}
+
+template <int WM_, int WN_, int WGM_, int WGN_, bool CPLX_, int MODE_, int STAGES_, int MINB_>
+struct Tile {
+  static constexpr int WM = WM_, WN = WN_, WGM = WGM_, WGN = WGN_, MODE = MODE_, STAGES = STAGES_, MINB = MINB_;
+  static constexpr bool CPLX = CPLX_;
+  static constexpr int W = CPLX ? 2 : 1;
+  static constexpr int BM = WGM * WM * 8;          // rows (ordered pairs, or basis rows in vector mode)
+  static constexpr int BN = WGN * WN * 8;          // real columns
+  static constexpr int BI = BM / 8;                // matrix mode: i rows per tile (8 j rows)
+  static constexpr int LDB = BN + 4;               // == 4 or 12 (mod 16): conflict-free B fragments
+  static constexpr int BIP = BI + 2;               // i-side pitch (even)
+  static constexpr int NJ = (MODE == MODE_MATRIX) ? 8 : BM;    // weighted-side rows
+  static constexpr int PJP = NJ + 4;               // == 12 (mod 16) resp. 4 (mod 16)
+  static constexpr int NE = (MODE == MODE_MATRIX) ? BI + 8 : BM;   // staged basis rows
+  static_assert(WGM * WGN * 32 == NT, "8 warps");
+  static_assert(BN % 8 == 0 && (LDB % 16 == 4 || LDB % 16 == 12), "B pitch");
+  static size_t smem_bytes(int tsz, int nvars) {
+    size_t d = (size_t)(tsz + ZPAD) * W + (size_t)STAGES * KQ * LDB + (size_t)2 * W * KQ * PJP;
+    if (MODE == MODE_MATRIX) d += (size_t)2 * W * KQ * BIP;
+    size_t b = d * 8 + 32 + (size_t)NE * nvars * 2 + (size_t)NT * 32;
+    return (b + 15) & ~(size_t)15;
+  }
+};
+
+template <class TL>
+__global__ void __launch_bounds__(NT, TL::MINB) k_project(const __grid_constant__ ProjParams p) {
+  constexpr int WM = TL::WM, WN = TL::WN, WGN = TL::WGN, W = TL::W, BM = TL::BM, BN = TL::BN, BI = TL::BI;
+  constexpr int LDB = TL::LDB, BIP = TL::BIP, PJP = TL::PJP, NE = TL::NE, STAGES = TL::STAGES;
+  constexpr bool CPLX = TL::CPLX;
+  constexpr bool MAT = TL::MODE == MODE_MATRIX;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *Ts = reinterpret_cast<double *>(smem_raw);                 // (tsz + ZPAD) * W
+  double *Bs = Ts + (size_t)(p.tsz + ZPAD) * W;                      // STAGES * KQ * LDB
+  if ((((size_t)(p.tsz + ZPAD) * W) & 1) != 0) Bs += 1;              // keep 16-byte alignment (slack is in the size)
+  double *Pj = Bs + (size_t)STAGES * KQ * LDB;                       // [2][W][KQ][PJP]
+  double *Pi = Pj + (size_t)2 * W * KQ * PJP;                        // [2][W][KQ][BIP]   (matrix mode)
+  unsigned short *eoff = reinterpret_cast<unsigned short *>(Pi + (MAT ? (size_t)2 * W * KQ * BIP : 0));  // [NE][nvars]
+  unsigned char *digs = reinterpret_cast<unsigned char *>(                                              // [NT][32], 16-B aligned
+      (reinterpret_cast<size_t>(eoff + (size_t)NE * p.nvars) + 15) & ~(size_t)15);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wgm = warp / WGN, wgn = warp % WGN;
+  const int g = lane >> 2, kl = lane & 3;
+
+  // ---- tile coordinates --------------------------------------------------------------------------
+  int t = blockIdx.x;
+  const int tn = t % p.tiles_n; t /= p.tiles_n;
+  const int tj = t % p.tiles_j; t /= p.tiles_j;
+  const int ti = t;
+  const int ibase = p.i0 + ti * BI;                       // matrix: first i of the tile
+  const int jbase = p.j0 + tj * TL::NJ;                   // first weighted-side basis row
+  const int iend = p.i0 + p.ni, jend = p.j0 + p.nj;
+  const int col0 = tn * BN;
+
+  // ---- q-slice of this CTA -----------------------------------------------------------------------
+  const long long nchunk_all = (p.q1 - p.q0 + KQ - 1) / KQ;
+  const long long c_begin = blockIdx.y * p.chunks_per_slice;
+  const long long c_end = min(nchunk_all, c_begin + p.chunks_per_slice);
+  const int nchunk = (int)max(0LL, c_end - c_begin);
+
+  // ---- one-time staging: 1-D tables and per-row table offsets ------------------------------------
+  for (int i = tid; i < p.tsz * W; i += NT) Ts[i] = p.T[i];
+  for (int i = tid; i < ZPAD * W; i += NT) Ts[p.tsz * W + i] = 0.0;
+  for (int e = tid; e < NE * p.nvars; e += NT) {
+    const int r = e / p.nvars, d = e % p.nvars;
+    int k;
+    bool ok;
+    if (MAT) {
+      if (r < BI) { k = ibase + r; ok = k < iend; }
+      else { k = jbase + (r - BI); ok = k < jend; }
+    } else { k = jbase + r; ok = k < jend; }
+    // invalid rows point at the zero pad for variable 0 (product becomes 0), anywhere valid otherwise
+    int off = ok ? p.toff[d] + p.deg[(size_t)k * p.nvars + d] * p.nq[d] : (d == 0 ? p.tsz : p.toff[d]);
+    eoff[e] = (unsigned short)off;
+  }
+
+  // ---- producers ---------------------------------------------------------------------------------
+  auto issue_B = [&](int c) {   // chunk c (relative to this slice) -> stage c % STAGES
+    if (c < nchunk) {
+      double *dst = Bs + (size_t)(c % STAGES) * KQ * LDB;
+      const long long r0 = (c_begin + c) * KQ;            // row of J relative to q0
+      const long long nrows = p.q1 - p.q0;
+      if (p.vec16) {
+        for (int idx = tid; idx < KQ * (BN / 2); idx += NT) {
+          const int row = idx / (BN / 2), ch = idx % (BN / 2);
+          const int col = col0 + ch * 2;
+          int bytes = (p.ncols_d - col) * 8;
+          bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+          if (r0 + row >= nrows) bytes = 0;
+          const double *src = bytes ? p.in + (r0 + row) * p.ld_in + col : p.in;
+          cp_async16(dst + row * LDB + ch * 2, src, bytes);
+        }
+      } else {
+        for (int idx = tid; idx < KQ * BN; idx += NT) {
+          const int row = idx / BN, ch = idx % BN;
+          const int col = col0 + ch;
+          int bytes = (col < p.ncols_d && r0 + row < nrows) ? 8 : 0;
+          const double *src = bytes ? p.in + (r0 + row) * p.ld_in + col : p.in;
+          cp_async8(dst + row * LDB + ch, src, bytes);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  // digits + weight of "my" quadrature point of a chunk (lane = point, warp = row group)
+  uint4 dg0 = make_uint4(0, 0, 0, 0), dg1 = make_uint4(0, 0, 0, 0);
+  double wre = 0.0, wim = 0.0;
+  auto fetch_point = [&](int c) {
+    if (c < nchunk) {
+      long long q = p.q0 + (c_begin + c) * KQ + lane;
+      const bool ok = q < p.q1;
+      if (!ok) q = p.q1 - 1;
+      const uint4 *src = reinterpret_cast<const uint4 *>(p.qdig + q * p.DP);
+      dg0 = __ldg(src);
+      if (p.DP == 32) dg1 = __ldg(src + 1);
+      if (CPLX) { wre = ok ? __ldg(p.W + 2 * q) : 0.0; wim = ok ? __ldg(p.W + 2 * q + 1) : 0.0; }
+      else wre = ok ? __ldg(p.W + q) : 0.0;
+    }
+  };
+
+  unsigned char *mydig = digs + tid * 32;
+  auto stage_psi = [&](int buf) {
+    // publish my digits to my private smem slot (dynamic byte indexing without local memory)
+    *reinterpret_cast<uint4 *>(mydig) = dg0;
+    if (p.DP == 32) *reinterpret_cast<uint4 *>(mydig + 16) = dg1;
+    double *pj = Pj + (size_t)buf * W * KQ * PJP;
+    double *pi = Pi + (size_t)buf * W * KQ * BIP;
+    for (int e = warp; e < NE; e += NT / 32) {
+      const unsigned short *eo = eoff + e * p.nvars;
+      double vr = 1.0, vi = 0.0;
+      if (!CPLX) {
+        for (int d = 0; d < p.nvars; d++) vr *= Ts[eo[d] + mydig[d]];
+      } else {
+        for (int d = 0; d < p.nvars; d++) {
+          const int o = 2 * (eo[d] + mydig[d]);
+          const double tr = Ts[o], tm = Ts[o + 1];
+          const double nr = vr * tr - vi * tm, ni = vr * tm + vi * tr;
+          vr = nr; vi = ni;
+        }
+      }
+      const bool weighted = !MAT || e >= BI;
+      if (weighted) {
+        if (!CPLX) vr *= wre;
+        else { const double nr = vr * wre - vi * wim, ni = vr * wim + vi * wre; vr = nr; vi = ni; }
+        const int r = MAT ? e - BI : e;
+        pj[lane * PJP + r] = vr;
+        if (CPLX) pj[KQ * PJP + lane * PJP + r] = vi;
+      } else {
+        pi[lane * BIP + e] = vr;
+        if (CPLX) pi[KQ * BIP + lane * BIP + e] = vi;
+      }
+    }
+  };
+
+  // ---- accumulators ------------------------------------------------------------------------------
+  double acc[WM][WN][2];
+#pragma unroll
+  for (int a = 0; a < WM; a++)
+#pragma unroll
+    for (int b = 0; b < WN; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+  const unsigned sgn = (g & 1) ? 0u : 0x80000000u;   // complex: even real-column (re part) takes -B_im
+
+  // ---- pipeline ----------------------------------------------------------------------------------
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) issue_B(s);
+  fetch_point(0);
+  __syncthreads();   // tables + eoff visible
+
+  for (int c = 0; c < nchunk; c++) {
+    const int buf = c & 1;
+    stage_psi(buf);
+    fetch_point(c + 1);
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    issue_B(c + STAGES - 1);
+
+    const double *bs = Bs + (size_t)(c % STAGES) * KQ * LDB + wgn * WN * 8 + g;
+    const double *pj = Pj + (size_t)buf * W * KQ * PJP;
+    const double *pi = Pi + (size_t)buf * W * KQ * BIP;
+#pragma unroll
+    for (int ks = 0; ks < KQ / 4; ks++) {
+      const int k = ks * 4 + kl;
+      double are[WM], aim[WM];
+      if (MAT) {
+        const double ajr = pj[k * PJP + g];
+        const double aji = CPLX ? pj[KQ * PJP + k * PJP + g] : 0.0;
+#pragma unroll
+        for (int a = 0; a < WM; a++) {
+          const double air = pi[k * BIP + wgm * WM + a];
+          if (!CPLX) are[a] = air * ajr;
+          else {
+            const double aii = pi[KQ * BIP + k * BIP + wgm * WM + a];
+            are[a] = air * ajr - aii * aji;
+            aim[a] = air * aji + aii * ajr;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int a = 0; a < WM; a++) {
+          are[a] = pj[k * PJP + (wgm * WM + a) * 8 + g];
+          if (CPLX) aim[a] = pj[KQ * PJP + k * PJP + (wgm * WM + a) * 8 + g];
+        }
+      }
+      double bfr[WN], bsw[WN];
+#pragma unroll
+      for (int b = 0; b < WN; b++) {
+        bfr[b] = bs[k * LDB + b * 8];
+        if (CPLX) bsw[b] = flip_sign(bs[k * LDB + b * 8 + ((g & 1) ? -1 : 1)], sgn);
+      }
+#pragma unroll
+      for (int a = 0; a < WM; a++)
+#pragma unroll
+        for (int b = 0; b < WN; b++) {
+          dmma884(acc[a][b][0], acc[a][b][1], are[a], bfr[b]);
+          if (CPLX) dmma884(acc[a][b][0], acc[a][b][1], aim[a], bsw[b]);
+        }
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue: lane owns rows g of each 8-row tile, columns 2*kl, 2*kl+1 of each 8-column tile ----
+  double *outp = p.out + (long long)blockIdx.y * p.slice_stride;
+#pragma unroll
+  for (int a = 0; a < WM; a++) {
+    long long rowoff;
+    bool rok;
+    if (MAT) {
+      const int i = ibase + wgm * WM + a, j = jbase + g;
+      rok = i < iend && j < jend;
+      rowoff = (long long)(i - p.i0) * p.stride_i + (long long)(j - p.j0) * p.stride_j;
+    } else {
+      const int k = jbase + (wgm * WM + a) * 8 + g;
+      rok = k < jend;
+      rowoff = (long long)(k - p.j0) * p.stride_j;
+    }
+    if (!rok) continue;
+#pragma unroll
+    for (int b = 0; b < WN; b++) {
+      const int col = col0 + wgn * WN * 8 + b * 8 + 2 * kl;
+      double *dst = outp + rowoff + col;
+      double v0 = acc[a][b][0], v1 = acc[a][b][1];
+      if (col + 1 < p.ncols_d && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
+        if (p.accumulate) { const double2 o = *reinterpret_cast<double2 *>(dst); v0 += o.x; v1 += o.y; }
+        *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
+      } else {
+        if (col < p.ncols_d) dst[0] = p.accumulate ? dst[0] + v0 : v0;
+        if (col + 1 < p.ncols_d) dst[1] = p.accumulate ? dst[1] + v1 : v1;
+      }
+    }
+  }
+}
+
+// sums the ksplit partial windows in slice order (deterministic) into the output
+__global__ void k_reduce_slices(const double *ws, long long slice_stride, int ksplit, double *out, long long n,
+                                int accumulate) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += step) {
+    double s = ws[i];
+    for (int k = 1; k < ksplit; k++) s += ws[i + k * slice_stride];
+    out[i] = accumulate ? out[i] + s : s;
+  }
+}
+
+// ---- host-side planning ----------------------------------------------------------------------------
+struct Variant {
+  int id, BM, BN, BI, NJ, minb;
+  const char *name;
+};
+
+struct Plan {
+  int variant_idx;
+  int tiles_i, tiles_j, tiles_n, ksplit;
+  long long chunks_per_slice, nchunk;
+  size_t ws_bytes;
+  long long out_elems;
+};
+
+template <class TL> int launch(const pspace_ctx *c, ProjParams &p, dim3 grid, cudaStream_t st) {
+  size_t smem = TL::smem_bytes(c->tsz, c->nvars);
+  if (smem > 227 * 1024) return ps_fail(PSPACE_EINVAL, "1-D tables too large for the staged kernel (%zu B shared memory)", smem);
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    PS_CUDA(cudaFuncSetAttribute(k_project<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  k_project<TL><<<grid, NT, smem, st>>>(p);
+  PS_LAUNCH_CHECK(c);
+  return PSPACE_OK;
+}
+
+//                         WM WN WGM WGN cplx   mode         stages minb
+typedef Tile<4, 6, 4, 2, false, MODE_MATRIX, 4, 1> M96;     // 128 pairs x 96 cols   (m*m = 576 = 6 x 96)
+typedef Tile<4, 4, 4, 2, false, MODE_MATRIX, 4, 1> M64;     // 128 x 64              (m*m = 64)
+typedef Tile<4, 2, 8, 1, false, MODE_MATRIX, 4, 1> M16;     // 256 x 16
+typedef Tile<4, 1, 8, 1, false, MODE_MATRIX, 4, 1> M8;      // 256 x 8               (scalar J)
+typedef Tile<4, 6, 4, 2, true, MODE_MATRIX, 4, 1> ZM96;
+typedef Tile<4, 4, 4, 2, true, MODE_MATRIX, 4, 1> ZM64;
+typedef Tile<4, 2, 8, 1, true, MODE_MATRIX, 4, 1> ZM16;
+typedef Tile<4, 1, 8, 1, true, MODE_MATRIX, 4, 1> ZM8;
+typedef Tile<2, 4, 8, 1, false, MODE_VECTOR, 4, 1> V32;     // 128 basis rows x 32 cols
+typedef Tile<2, 1, 8, 1, false, MODE_VECTOR, 4, 1> V8;
+typedef Tile<2, 4, 8, 1, true, MODE_VECTOR, 4, 1> ZV32;
+typedef Tile<2, 1, 8, 1, true, MODE_VECTOR, 4, 1> ZV8;
+
+const Variant MAT_VARIANTS[] = {{1, M96::BM, M96::BN, M96::BI, 8, 1, "dmma 128x96"},
+                                {2, M64::BM, M64::BN, M64::BI, 8, 1, "dmma 128x64"},
+                                {3, M16::BM, M16::BN, M16::BI, 8, 1, "dmma 256x16"},
+                                {4, M8::BM, M8::BN, M8::BI, 8, 1, "dmma 256x8"}};
+const Variant VEC_VARIANTS[] = {{1, V32::BM, V32::BN, 0, V32::BM, 1, "dmma vec 128x32"},
+                                {2, V8::BM, V8::BN, 0, V8::BM, 1, "dmma vec 128x8"}};
+
+int sm_count(int device) {
+  static int cached[64] = {0};
+  if (device < 64 && cached[device]) return cached[device];
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+  if (device < 64) cached[device] = n;
+  return n;
+}
+
+int make_plan(const pspace_ctx *c, int is_matrix, const pspace_project_args *a, Plan &pl) {
+  if (!c->tables_ready) return ps_fail(PSPACE_ESTATE, "project called before initializeBasis + initializeQuadrature");
+  if (a->ncols < 1) return ps_fail(PSPACE_EINVAL, "ncols must be >= 1");
+  if (a->q0 < 0 || a->q1 > c->Q || a->q1 < a->q0) return ps_fail(PSPACE_EINVAL, "q range [%lld,%lld) outside [0,%lld)", a->q0, a->q1, c->Q);
+  if (a->k0 < 0 || a->k1 > c->N || a->k1 < a->k0) return ps_fail(PSPACE_EINVAL, "basis range [%d,%d) outside [0,%d)", a->k0, a->k1, c->N);
+  if (is_matrix && (a->j0 < 0 || a->j1 > c->N || a->j1 < a->j0)) return ps_fail(PSPACE_EINVAL, "j range [%d,%d) outside [0,%d)", a->j0, a->j1, c->N);
+  const int ncols_d = a->ncols * c->width;
+  const Variant *vs = is_matrix ? MAT_VARIANTS : VEC_VARIANTS;
+  const int nv = is_matrix ? 4 : 2;
+  int best = -1;
+  if (a->variant > 0) {
+    for (int i = 0; i < nv; i++) if (vs[i].id == a->variant) best = i;
+    if (best < 0) return ps_fail(PSPACE_EINVAL, "unknown tile variant %d", a->variant);
+  } else {
+    double bestcost = 0;
+    for (int i = 0; i < nv; i++) {
+      // padded work; ties go to the earlier (wider) variant
+      double padn = (double)((ncols_d + vs[i].BN - 1) / vs[i].BN) * vs[i].BN;
+      double padm;
+      if (is_matrix) padm = (double)((a->k1 - a->k0 + vs[i].BI - 1) / vs[i].BI) * vs[i].BI * ((a->j1 - a->j0 + 7) / 8) * 8;
+      else padm = (double)((a->k1 - a->k0 + vs[i].BM - 1) / vs[i].BM) * vs[i].BM;
+      double cost = padn * padm;
+      if (best < 0 || cost < bestcost * 0.999) { best = i; bestcost = cost; }
+    }
+  }
+  const Variant &v = vs[best];
+  pl.variant_idx = best;
+  pl.tiles_n = (ncols_d + v.BN - 1) / v.BN;
+  if (is_matrix) {
+    pl.tiles_i = (a->k1 - a->k0 + v.BI - 1) / v.BI;
+    pl.tiles_j = (a->j1 - a->j0 + 7) / 8;
+    pl.out_elems = (long long)(a->k1 - a->k0) * (a->j1 - a->j0) * ncols_d;
+  } else {
+    pl.tiles_i = 1;
+    pl.tiles_j = (a->k1 - a->k0 + v.BM - 1) / v.BM;
+    pl.out_elems = (long long)(a->k1 - a->k0) * ncols_d;
+  }
+  pl.nchunk = (a->q1 - a->q0 + KQ - 1) / KQ;
+  long long ntiles = (long long)pl.tiles_i * pl.tiles_j * pl.tiles_n;
+  int ks = 1;
+  if (a->ksplit > 0) ks = a->ksplit;
+  else if (ntiles > 0) {
+    // fill ~2 waves of the machine, but keep >= 8 chunks (256 points) per slice
+    const long long target = 2LL * sm_count(c->device) * v.minb;
+    if (ntiles < target) ks = (int)std::min<long long>((target + ntiles - 1) / ntiles, std::max<long long>(1, pl.nchunk / 8));
+  }
+  if (ks > pl.nchunk) ks = (int)std::max<long long>(1, pl.nchunk);
+  if (ks > 65535) ks = 65535;
+  pl.chunks_per_slice = ks > 0 ? (pl.nchunk + ks - 1) / ks : 0;
+  if (pl.chunks_per_slice > 0) ks = (int)((pl.nchunk + pl.chunks_per_slice - 1) / pl.chunks_per_slice);
+  pl.ksplit = std::max(1, ks);
+  pl.ws_bytes = pl.ksplit > 1 ? (size_t)pl.ksplit * pl.out_elems * sizeof(double) : 0;
+  return PSPACE_OK;
+}
+}  // namespace
+
+size_t ps_project_workspace(const pspace_ctx *c, int is_matrix, const pspace_project_args *a) {
+  Plan pl;
+  if (make_plan(c, is_matrix, a, pl) != PSPACE_OK) return 0;
+  return pl.ws_bytes;
+}
+
+int ps_project(const pspace_ctx *c, int is_matrix, const pspace_project_args *a, const double *d_in, double *d_out,
+               void *d_ws, size_t ws_bytes, cudaStream_t st) {
+  Plan pl;
+  int rc = make_plan(c, is_matrix, a, pl);
+  if (rc) return rc;
+  pspace_ctx *mc = const_cast<pspace_ctx *>(c);
+  const int ncols_d = a->ncols * c->width;
+  if (pl.out_elems == 0) return PSPACE_OK;
+  if (pl.nchunk == 0) {   // empty q range: the projection is zero
+    if (!a->accumulate) PS_CUDA(cudaMemsetAsync(d_out, 0, pl.out_elems * sizeof(double), st));
+    return PSPACE_OK;
+  }
+  if (pl.ws_bytes > ws_bytes || (pl.ws_bytes && !d_ws))
+    return ps_fail(PSPACE_EINVAL, "workspace of %zu bytes needed, %zu given", pl.ws_bytes, ws_bytes);
+
+  ProjParams p;
+  p.in = d_in;
+  p.ld_in = ncols_d;
+  p.q0 = a->q0; p.q1 = a->q1;
+  p.ncols_d = ncols_d;
+  p.nvars = c->nvars; p.tsz = c->tsz; p.DP = c->DP;
+  p.T = c->d_T; p.deg = c->d_deg; p.qdig = c->d_qdig; p.W = c->d_W;
+  for (int d = 0; d < c->nvars; d++) { p.toff[d] = c->toff[d]; p.nq[d] = c->nq[d]; }
+  p.tiles_n = pl.tiles_n; p.tiles_j = pl.tiles_j; p.tiles_i = pl.tiles_i;
+  p.chunks_per_slice = pl.chunks_per_slice;
+  p.vec16 = ((ncols_d % 2) == 0 && (reinterpret_cast<size_t>(d_in) % 16) == 0) ? 1 : 0;
+  if (is_matrix) {
+    p.i0 = a->k0; p.ni = a->k1 - a->k0; p.j0 = a->j0; p.nj = a->j1 - a->j0;
+    p.stride_j = ncols_d; p.stride_i = (long long)p.nj * ncols_d;
+  } else {
+    p.i0 = 0; p.ni = 1; p.j0 = a->k0; p.nj = a->k1 - a->k0;
+    p.stride_j = ncols_d; p.stride_i = 0;
+  }
+  const bool split = pl.ksplit > 1;
+  p.out = split ? (double *)d_ws : d_out;
+  p.slice_stride = split ? pl.out_elems : 0;
+  p.accumulate = split ? 0 : a->accumulate;
+
+  dim3 grid((unsigned)((long long)pl.tiles_i * pl.tiles_j * pl.tiles_n), (unsigned)pl.ksplit);
+  const Variant &v = (is_matrix ? MAT_VARIANTS : VEC_VARIANTS)[pl.variant_idx];
+  const int key = (is_matrix ? 0 : 100) + (c->is_complex ? 10 : 0) + v.id;
+  switch (key) {
+    case 1: rc = launch<M96>(c, p, grid, st); break;
+    case 2: rc = launch<M64>(c, p, grid, st); break;
+    case 3: rc = launch<M16>(c, p, grid, st); break;
+    case 4: rc = launch<M8>(c, p, grid, st); break;
+    case 11: rc = launch<ZM96>(c, p, grid, st); break;
+    case 12: rc = launch<ZM64>(c, p, grid, st); break;
+    case 13: rc = launch<ZM16>(c, p, grid, st); break;
+    case 14: rc = launch<ZM8>(c, p, grid, st); break;
+    case 101: rc = launch<V32>(c, p, grid, st); break;
+    case 102: rc = launch<V8>(c, p, grid, st); break;
+    case 111: rc = launch<ZV32>(c, p, grid, st); break;
+    case 112: rc = launch<ZV8>(c, p, grid, st); break;
+    default: rc = ps_fail(PSPACE_EINVAL, "no kernel for key %d", key);
+  }
+  if (rc) return rc;
+  if (split) {
+    long long n = pl.out_elems;
+    unsigned nb = (unsigned)std::min<long long>((n + 255) / 256, 148LL * 16);
+    k_reduce_slices<<<nb, 256, 0, st>>>((const double *)d_ws, pl.out_elems, pl.ksplit, d_out, n, a->accumulate);
+    PS_LAUNCH_CHECK(c);
+  }
+  // plan record (bench / DESIGN): executed FLOP = 2 * rows * cols * q per real FMA, x2 again for the two
+  // DMMA passes of the complex build (= 8 FLOP per complex FMA)
+  const double rows = is_matrix ? (double)p.ni * p.nj : (double)p.nj;
+  mc->plan_flop = 2.0 * rows * (double)ncols_d * (double)(a->q1 - a->q0) * (c->is_complex ? 2.0 : 1.0);
+  char buf[256];
+  snprintf(buf, sizeof buf, "%s%s tiles=%dx%dx%d ksplit=%d chunks/slice=%lld stages=4 smem=%zuB", c->is_complex ? "z " : "",
+           v.name, pl.tiles_i, pl.tiles_j, pl.tiles_n, pl.ksplit, pl.chunks_per_slice, (size_t)0);
+  mc->plan = buf;
+  return PSPACE_OK;
+}

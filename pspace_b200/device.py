@@ -1,0 +1,228 @@
+"""DeviceContainer — Python handle on the device-side state of one ParameterContainer.
+
+This is the layer the tests, smoke() and bench.py drive: it owns a `pspace_ctx*` of the C-ABI and moves
+data with torch (device memory, streams).  Names follow the reference container
+(src/include/ParameterContainer.h:17-41): initialize / initializeBasis / initializeQuadrature /
+getNumBasisTerms / getNumQuadraturePoints / getBasisParamDeg / quadrature / basis, plus the batched
+additions projectVector / projectMatrix / evalBasis.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import cabi
+from .cabi import ProjectArgs, check
+
+KIND = {"normal": 0, "uniform": 1, "exponential": 2}
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DeviceContainer:
+    def __init__(self, params, basis_type=0, complex_=False, device=0):
+        """params: [(kind, p1, p2, dmax)] in ParameterFactory order (ids 0..nvars-1)."""
+        self.L = cabi.lib()
+        self.is_complex = bool(complex_)
+        self.np_dtype = np.complex128 if complex_ else np.float64
+        self.t_dtype = torch.complex128 if complex_ else torch.float64
+        self.device = torch.device("cuda", device)
+        self.nvars = len(params)
+        kinds = np.array([KIND[p[0]] if isinstance(p[0], str) else int(p[0]) for p in params], dtype=np.intc)
+        p1 = np.array([p[1] for p in params], dtype=self.np_dtype)
+        p2 = np.array([p[2] for p in params], dtype=self.np_dtype)
+        dmax = np.array([p[3] for p in params], dtype=np.intc)
+        h = ctypes.c_void_p()
+        check(self.L.pspace_cuda_create(ctypes.byref(h), device, int(complex_), self.nvars, cabi.np_ptr(kinds),
+                                        cabi.np_ptr(p1), cabi.np_ptr(p2), cabi.np_ptr(dmax), basis_type))
+        self.h = h
+        self._ws = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pspace_cuda_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- initialisation (ParameterContainer.cpp:84-160, 224-237) ---------------------------------
+    def initialize(self):
+        with torch.cuda.device(self.device):
+            check(self.L.pspace_cuda_initialize(self.h, _stream_ptr()))
+        return self
+
+    def initializeBasis(self, pmax):
+        a = np.ascontiguousarray(pmax, dtype=np.intc)
+        with torch.cuda.device(self.device):
+            check(self.L.pspace_cuda_initialize_basis(self.h, cabi.np_ptr(a), _stream_ptr()))
+        return self
+
+    def initializeQuadrature(self, nqpts):
+        a = np.ascontiguousarray(nqpts, dtype=np.intc)
+        with torch.cuda.device(self.device):
+            check(self.L.pspace_cuda_initialize_quadrature(self.h, cabi.np_ptr(a), _stream_ptr()))
+        return self
+
+    # ---- accessors -------------------------------------------------------------------------------
+    def getNumBasisTerms(self):
+        return self.L.pspace_cuda_num_basis(self.h)
+
+    def getNumQuadraturePoints(self):
+        return self.L.pspace_cuda_num_quad(self.h)
+
+    def getNumParameters(self):
+        return self.L.pspace_cuda_num_params(self.h)
+
+    N = property(getNumBasisTerms)
+    Q = property(getNumQuadraturePoints)
+
+    def degrees(self):
+        out = np.zeros((self.N, self.nvars), dtype=np.intc)
+        check(self.L.pspace_cuda_get_degrees(self.h, cabi.np_ptr(out)))
+        return out
+
+    def getBasisParamDeg(self, k):
+        return self.degrees()[k].copy()
+
+    def rules(self, pid, n):
+        z = np.zeros(n, dtype=self.np_dtype); y = np.zeros(n, dtype=self.np_dtype); w = np.zeros(n, dtype=self.np_dtype)
+        check(self.L.pspace_cuda_get_rules(self.h, pid, cabi.np_ptr(z), cabi.np_ptr(y), cabi.np_ptr(w)))
+        return z, y, w
+
+    def table(self, pid, rows, n):
+        T = np.zeros((rows, n), dtype=self.np_dtype)
+        check(self.L.pspace_cuda_get_table(self.h, pid, cabi.np_ptr(T)))
+        return T
+
+    def weights(self, q0=0, q1=None):
+        q1 = self.Q if q1 is None else q1
+        W = np.zeros(q1 - q0, dtype=self.np_dtype)
+        check(self.L.pspace_cuda_get_weights(self.h, q0, q1, cabi.np_ptr(W)))
+        return W
+
+    def grid(self, q0=0, q1=None):
+        """Materialised (Z, Y, W) for q in [q0,q1) as device tensors, point-major."""
+        q1 = self.Q if q1 is None else q1
+        n = q1 - q0
+        Z = torch.empty((n, self.nvars), dtype=self.t_dtype, device=self.device)
+        Y = torch.empty((n, self.nvars), dtype=self.t_dtype, device=self.device)
+        W = torch.empty((n,), dtype=self.t_dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.L.pspace_cuda_tensor_grid(self.h, q0, q1, Z.data_ptr(), Y.data_ptr(), W.data_ptr(), _stream_ptr()))
+        return Z, Y, W
+
+    # ---- batched basis evaluation ------------------------------------------------------------------
+    def evalBasisGrid(self, k0=0, k1=None, q0=0, q1=None):
+        k1 = self.N if k1 is None else k1
+        q1 = self.Q if q1 is None else q1
+        psi = torch.empty((k1 - k0, q1 - q0), dtype=self.t_dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.L.pspace_cuda_eval_basis_grid(self.h, k0, k1, q0, q1, psi.data_ptr(), _stream_ptr()))
+        return psi
+
+    def evalBasis(self, z, k0=0, k1=None):
+        """psi[k][p] = basis(k, z_p) for arbitrary points z [npts][nvars] (device or host array)."""
+        k1 = self.N if k1 is None else k1
+        zt = torch.as_tensor(z, dtype=self.t_dtype).reshape(-1, self.nvars).contiguous().to(self.device)
+        psi = torch.empty((k1 - k0, zt.shape[0]), dtype=self.t_dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.L.pspace_cuda_eval_basis_points(self.h, k0, k1, zt.shape[0], zt.data_ptr(), psi.data_ptr(), _stream_ptr()))
+        return psi
+
+    # ---- projections ---------------------------------------------------------------------------------
+    def _args(self, k0, k1, j0, j1, q0, q1, ncols, accumulate, ksplit, variant):
+        return ProjectArgs(k0, k1, j0, j1, q0, q1, ncols, int(accumulate), ksplit, variant)
+
+    def _workspace(self, is_matrix, a):
+        need = self.L.pspace_cuda_project_workspace(self.h, is_matrix, ctypes.byref(a))
+        if need == 0:
+            return None, 0
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws, need
+
+    def projectVector(self, f, k0=0, k1=None, q0=0, q1=None, out=None, accumulate=False, ksplit=0, variant=0):
+        """F[k][c] = sum_q w_q psi_k(z_q) f[q][c]; f holds rows q0..q1-1 (device tensor [q1-q0][m])."""
+        k1 = self.N if k1 is None else k1
+        q1 = self.Q if q1 is None else q1
+        assert f.is_cuda and f.dtype == self.t_dtype and f.is_contiguous() and f.shape[0] == q1 - q0
+        m = f.shape[1]
+        if out is None:
+            out = torch.empty((k1 - k0, m), dtype=self.t_dtype, device=self.device)
+        a = self._args(k0, k1, 0, 0, q0, q1, m, accumulate, ksplit, variant)
+        ws, need = self._workspace(0, a)
+        with torch.cuda.device(self.device):
+            check(self.L.pspace_cuda_project_vector(self.h, ctypes.byref(a), f.data_ptr(), out.data_ptr(),
+                                                    ws.data_ptr() if ws is not None else None, need, _stream_ptr()))
+        return out
+
+    def projectMatrix(self, J, i0=0, i1=None, j0=0, j1=None, q0=0, q1=None, out=None, accumulate=False, ksplit=0,
+                      variant=0):
+        """C[i][j][c] = sum_q w_q psi_i psi_j J[q][c]; J holds rows q0..q1-1 (device tensor [q1-q0][m2])."""
+        i1 = self.N if i1 is None else i1
+        j1 = self.N if j1 is None else j1
+        q1 = self.Q if q1 is None else q1
+        assert J.is_cuda and J.dtype == self.t_dtype and J.is_contiguous() and J.shape[0] == q1 - q0
+        m2 = J.shape[1]
+        if out is None:
+            out = torch.empty((i1 - i0, j1 - j0, m2), dtype=self.t_dtype, device=self.device)
+        a = self._args(i0, i1, j0, j1, q0, q1, m2, accumulate, ksplit, variant)
+        ws, need = self._workspace(1, a)
+        with torch.cuda.device(self.device):
+            check(self.L.pspace_cuda_project_matrix(self.h, ctypes.byref(a), J.data_ptr(), out.data_ptr(),
+                                                    ws.data_ptr() if ws is not None else None, need, _stream_ptr()))
+        return out
+
+    def projectMatrixHost(self, J, i0=0, i1=None, j0=0, j1=None, q0=0, q1=None, out=None, accumulate=False):
+        """Host-buffer form (numpy or pinned torch CPU tensors in/out); copies are inside the call."""
+        i1 = self.N if i1 is None else i1
+        j1 = self.N if j1 is None else j1
+        q1 = self.Q if q1 is None else q1
+        Jn = J.numpy() if isinstance(J, torch.Tensor) else np.ascontiguousarray(J, dtype=self.np_dtype)
+        m2 = Jn.shape[1]
+        if out is None:
+            out = np.zeros((i1 - i0, j1 - j0, m2), dtype=self.np_dtype)
+        on = out.numpy() if isinstance(out, torch.Tensor) else out
+        a = self._args(i0, i1, j0, j1, q0, q1, m2, accumulate, 0, 0)
+        check(self.L.pspace_cuda_project_matrix_host(self.h, ctypes.byref(a), Jn.ctypes.data, on.ctypes.data))
+        return out
+
+    def projectVectorHost(self, f, k0=0, k1=None, q0=0, q1=None, out=None, accumulate=False):
+        k1 = self.N if k1 is None else k1
+        q1 = self.Q if q1 is None else q1
+        fn = f.numpy() if isinstance(f, torch.Tensor) else np.ascontiguousarray(f, dtype=self.np_dtype)
+        m = fn.shape[1]
+        if out is None:
+            out = np.zeros((k1 - k0, m), dtype=self.np_dtype)
+        on = out.numpy() if isinstance(out, torch.Tensor) else out
+        a = self._args(k0, k1, 0, 0, q0, q1, m, accumulate, 0, 0)
+        check(self.L.pspace_cuda_project_vector_host(self.h, ctypes.byref(a), fn.ctypes.data, on.ctypes.data))
+        return out
+
+    def launchCount(self):
+        return self.L.pspace_cuda_launch_count(self.h)
+
+    def lastPlan(self):
+        buf = ctypes.create_string_buffer(512)
+        check(self.L.pspace_cuda_last_plan(self.h, buf, 512))
+        return buf.value.decode()
+
+
+def fill_synthetic(n, seed, offset=0, device=0):
+    """Device tensor of n doubles: splitmix64 uniform(-0.5,0.5) (same stream of numbers as the oracle's)."""
+    out = torch.empty(n, dtype=torch.float64, device=torch.device("cuda", device))
+    with torch.cuda.device(device):
+        check(cabi.lib().pspace_cuda_fill_synthetic(out.data_ptr(), n, seed, offset, _stream_ptr()))
+    return out
+
+
+def fp64_peak(mode=1, ms_target=300.0, device=0):
+    v = ctypes.c_double()
+    check(cabi.lib().pspace_cuda_fp64_peak(device, mode, ms_target, ctypes.byref(v)))
+    return v.value

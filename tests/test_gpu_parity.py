@@ -1,0 +1,247 @@
+"""GPU parity tests: the CUDA path, driven through the C-ABI (pspace_b200.cabi / DeviceContainer), against
+(a) the golden vectors generated from the compiled reference and (b) the restated oracle on the same
+seeded inputs.
+
+Bars (BASELINE.json north_star): integer/index work bit-exact; FP64 <= 1e-12 relative.  What is asserted:
+  * degree tables .................. bit-exact
+  * real 1-D rules, grids (Z,Y,W), 1-D tables, basis values at grid / arbitrary points ... bit-exact
+    (Legendre degree >= 5 goes through a double-double integer power instead of libm pow: <= 4 ulp asserted)
+  * complex rules/tables/basis ...... <= 1e-14 relative (complex division is Smith's, not libgcc's)
+  * projected F / C ................. normwise max|C - C_ref| / max|C_ref| <= 1e-12  (summation
+    order differs from the reference's sequential q loop, element-wise error is meaningless for entries
+    that cancel to ~0)
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import harness as H  # noqa: E402
+from tests.util import golden_params, load_golden, normwise, same_bits  # noqa: E402
+
+TOL = 1e-12
+
+
+def _dc(params, basis_type, cplx):
+    from pspace_b200.device import DeviceContainer
+    return DeviceContainer(params, basis_type, cplx)
+
+
+def _synth(n, seed, cplx):
+    return H.synthetic(2 * n, seed).view(np.complex128) if cplx else H.synthetic(n, seed)
+
+
+def _ulps(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b) / np.maximum(np.spacing(np.abs(b)), 1e-300))
+
+
+CASES = ["cfg1_real", "cfg1_complex", "test_pspace_real", "test_pspace_complex", "cfg2_real", "cfg2_complex",
+         "cfg3_real", "highdeg_real", "highdeg_complex"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_container_against_golden(name):
+    g = load_golden(name)
+    cplx = bool(int(g["is_complex"]))
+    ps = golden_params(g)
+    c = _dc(ps, int(g["basis_type"]), cplx).initialize()
+    assert c.N == int(g["N"]) and c.Q == int(g["Q"])
+    # (1) integer kernel: bit-exact
+    assert np.array_equal(c.degrees(), g["degrees"])
+    # (2) grid
+    Z, Y, W = (t.cpu().numpy() for t in c.grid())
+    has_deg5_legendre = any(k == "uniform" and d >= 5 for k, _, _, d in ps)
+    if not cplx:
+        assert same_bits(W, g["W"])
+        if "Z" in g.files:
+            assert same_bits(Z, g["Z"]) and same_bits(Y, g["Y"])
+        else:
+            assert same_bits(Z[g["qsel"]], g["Z_sel"]) and same_bits(Y[g["qsel"]], g["Y_sel"])
+    else:
+        assert normwise(W, g["W"]) < 1e-14
+        Zg = g["Z"] if "Z" in g.files else None
+        if Zg is not None:
+            assert normwise(Z, Zg) < 1e-14 and normwise(Y, g["Y"]) < 1e-14
+    assert np.array_equal(c.weights(), W)
+    # (2b) batched basis evaluation
+    psi = c.evalBasisGrid().cpu().numpy()[:, g["qsel"]]
+    psi_arb = c.evalBasis(g["zarb"]).cpu().numpy()
+    if not cplx and not has_deg5_legendre:
+        assert same_bits(psi, g["psi_sel"])
+        assert same_bits(psi_arb, g["psi_arb"])
+    else:
+        assert normwise(psi, g["psi_sel"]) < 1e-13
+        assert normwise(psi_arb, g["psi_arb"]) < 1e-13
+    # (3) projections
+    m, seed, Q = int(g["m"]), int(g["seed"]), c.Q
+    f = _synth(Q * m, seed, cplx).reshape(Q, m)
+    J = _synth(Q * m * m, seed + 1000, cplx).reshape(Q, m * m)
+    fd, Jd = torch.from_numpy(f).cuda(), torch.from_numpy(J).cuda()
+    F = c.projectVector(fd).cpu().numpy()
+    assert normwise(F, g["F"]) < TOL
+    i0, i1, j0, j1 = (int(v) for v in g["win"])
+    C = c.projectMatrix(Jd, i0, i1, j0, j1).cpu().numpy()
+    assert C.shape == g["C"].shape
+    assert normwise(C, g["C"]) < TOL
+    # host-buffer entry points give the same answer
+    Ch = c.projectMatrixHost(J, i0, i1, j0, j1)
+    assert np.array_equal(Ch, C)
+    Fh = c.projectVectorHost(f)
+    assert np.array_equal(Fh, F)
+    c.close()
+
+
+def test_one_dimensional_rules_bit_exact():
+    """(z, y, w) of every 1-D rule, npoints 1..20, each family (one single-parameter container per rule)."""
+    for cplx in (False, True):
+        g = load_golden("onedim_z" if cplx else "onedim")
+        ps = golden_params(g)
+        if not cplx:
+            ps = [(k, float(np.real(a)), float(np.real(b)), d) for k, a, b, d in ps]
+        checked = 0
+        for pid, p in enumerate(ps):
+            for n in range(1, 21):
+                key = f"rule_{pid}_{n}"
+                if key not in g.files:
+                    continue
+                c1 = _dc([(p[0], p[1], p[2], 1)], 0, cplx).initializeQuadrature([n])
+                got = np.stack(c1.rules(0, n))
+                if not cplx:
+                    assert same_bits(got, g[key]), key
+                else:
+                    assert normwise(got, g[key]) < 1e-15, key
+                c1.close()
+                checked += 1
+        assert checked == 76
+
+
+def test_polynomials_d0_to_12_against_golden():
+    """unit polynomials of every family at arbitrary z, degrees 0..12 (golden from the compiled reference)."""
+    for cplx in (False, True):
+        g = load_golden("onedim_z" if cplx else "onedim")
+        ps = golden_params(g)
+        if not cplx:
+            ps = [(k, float(np.real(a)), float(np.real(b)), d) for k, a, b, d in ps]
+        for pid, p in enumerate(ps):
+            c = _dc([(p[0], p[1], p[2], 12)], 0, cplx).initializeBasis([12])
+            zs = g[f"z_{pid}"].reshape(-1, 1)
+            psi = c.evalBasis(zs).cpu().numpy()          # [13][9]
+            ref = g[f"poly_{pid}"]
+            if cplx:
+                assert normwise(psi, ref) < 1e-13, (pid, p[0])
+            elif p[0] == "uniform":
+                assert same_bits(psi[:5], ref[:5])
+                assert _ulps(psi[5:], ref[5:]) <= 4, (pid, _ulps(psi[5:], ref[5:]))
+            else:
+                assert same_bits(psi, ref), (pid, p[0])
+            c.close()
+
+
+def test_basis_degree_tables_bit_exact():
+    from pspace_b200 import cabi
+    import ctypes
+    g = load_golden("basis_degrees")
+    L = cabi.lib()
+    for idx in range(int(g["ncases"])):
+        pmax = np.ascontiguousarray(g[f"pmax_{idx}"], dtype=np.intc)
+        bt = int(g[f"bt_{idx}"])
+        ref = g[f"deg_{idx}"]
+        n = ctypes.c_longlong()
+        cabi.check(L.pspace_cuda_basis_count(len(pmax), pmax.ctypes.data, bt, ctypes.byref(n)))
+        assert n.value == ref.shape[0]
+        out = torch.zeros((n.value, len(pmax)), dtype=torch.int32, device="cuda")
+        nb = ctypes.c_int()
+        cabi.check(L.pspace_cuda_basis_degrees(len(pmax), pmax.ctypes.data, bt, ctypes.byref(nb), out.data_ptr(),
+                                               n.value, None))
+        assert nb.value == ref.shape[0]
+        assert np.array_equal(out.cpu().numpy(), ref), (pmax, bt)
+
+
+@pytest.mark.parametrize("nv,p,bt", [(6, 2, 1), (7, 2, 0), (8, 3, 0), (10, 3, 1), (9, 1, 0)])
+def test_basis_degrees_beyond_five_variables_vs_extended_oracle(nv, p, bt):
+    from pspace_b200.workloads import mixed_params
+    ps = mixed_params(nv, p)
+    o = H.CpuContainer(H.oracle_api(False), ps, bt).initialize_basis([p] * nv)
+    c = _dc(ps, bt, False).initializeBasis([p] * nv)
+    assert c.N == o.N
+    assert np.array_equal(c.degrees(), o.degrees())
+    c.close()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_random_windows_and_splits_vs_oracle(cplx):
+    """ragged windows, odd column counts, forced q-splits, accumulate, q-shards."""
+    rng = np.random.default_rng(5 + cplx)
+    ps = [("normal", 0.3 + (1e-30j if cplx else 0), 1.2, 3), ("exponential", 0.0, 0.5, 2), ("uniform", -1.0, 2.0, 4),
+          ("normal", -1.0, 0.4, 2)]
+    o = H.CpuContainer(H.oracle_api(cplx), ps, 1).initialize()
+    c = _dc(ps, 1, cplx).initialize()
+    assert (c.N, c.Q) == (o.N, o.Q)
+    for m2 in (1, 3, 8, 9, 25, 64, 100):
+        J = rng.normal(size=(o.Q, m2)).astype(o.dtype)
+        if cplx:
+            J = J + 1j * rng.normal(size=J.shape)
+        Jd = torch.from_numpy(J).cuda()
+        i0, i1 = sorted(rng.choice(o.N + 1, 2, replace=False))
+        j0, j1 = sorted(rng.choice(o.N + 1, 2, replace=False))
+        ref = o.project_matrix(J, i0, i1, j0, j1, nthreads=4)
+        for ksplit in (0, 1, 3):
+            C = c.projectMatrix(Jd, i0, i1, j0, j1, ksplit=ksplit).cpu().numpy()
+            assert normwise(C, ref) < TOL, (m2, ksplit)
+        # accumulate adds to what is there
+        base = torch.from_numpy(np.ascontiguousarray(ref)).cuda().clone()
+        C2 = c.projectMatrix(Jd, i0, i1, j0, j1, out=base, accumulate=True).cpu().numpy()
+        assert normwise(C2, 2 * ref) < TOL
+        # two q-shards add up to the whole (multi-GPU decomposition)
+        qs = int(rng.integers(1, o.Q))
+        Ca = c.projectMatrix(Jd[:qs].contiguous(), i0, i1, j0, j1, q0=0, q1=qs)
+        Cb = c.projectMatrix(Jd[qs:].contiguous(), i0, i1, j0, j1, q0=qs, q1=o.Q)
+        assert normwise((Ca + Cb).cpu().numpy(), ref) < TOL
+        # vector projection with the same column counts
+        f = J
+        F = c.projectVector(Jd).cpu().numpy()
+        assert normwise(F, o.project_vector(f)) < TOL, m2
+        k0, k1 = sorted(rng.choice(o.N + 1, 2, replace=False))
+        Fw = c.projectVector(Jd, k0, k1, ksplit=2).cpu().numpy()
+        assert normwise(Fw, o.project_vector(f, k0, k1)) < TOL
+    # empty ranges
+    assert c.projectMatrix(Jd, 2, 2, 0, 3).numel() == 0
+    z = c.projectMatrix(Jd[:0].contiguous(), 0, 2, 0, 2, q0=5, q1=5)
+    assert float(z.abs().max()) == 0.0
+    c.close()
+
+
+def test_every_tile_variant_matches():
+    rng = np.random.default_rng(11)
+    ps = [("normal", 0.0, 1.0, 3), ("uniform", 0.0, 1.0, 3), ("exponential", 0.0, 1.0, 3)]
+    o = H.CpuContainer(H.oracle_api(False), ps, 0).initialize()
+    c = _dc(ps, 0, False).initialize()
+    J = rng.normal(size=(o.Q, 40))
+    Jd = torch.from_numpy(J).cuda()
+    ref = o.project_matrix(J, 0, 20, 3, 30, nthreads=4)
+    for variant in (1, 2, 3, 4):
+        C = c.projectMatrix(Jd, 0, 20, 3, 30, variant=variant).cpu().numpy()
+        assert normwise(C, ref) < TOL, variant
+    refF = o.project_vector(J)
+    for variant in (1, 2):
+        F = c.projectVector(Jd, variant=variant).cpu().numpy()
+        assert normwise(F, refF) < TOL, variant
+    c.close()
+
+
+def test_error_paths_are_loud():
+    from pspace_b200.cabi import PspaceCudaError
+    ps = [("normal", 0.0, 1.0, 2)]
+    c = _dc(ps, 0, False)
+    with pytest.raises(PspaceCudaError):
+        c.projectVector(torch.zeros((3, 1), dtype=torch.float64, device="cuda"), 0, 0, 0, 3)   # not initialised
+    with pytest.raises(PspaceCudaError):
+        c.initializeQuadrature([21])
+    with pytest.raises(PspaceCudaError):
+        c.initializeBasis([25])
+    c.initialize()
+    with pytest.raises(PspaceCudaError):
+        c.projectVector(torch.zeros((3, 1), dtype=torch.float64, device="cuda"), 0, 9, 0, 3)   # k1 > N
+    c.close()
