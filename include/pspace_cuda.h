@@ -132,6 +132,10 @@ int pspace_cuda_project_matrix_host(pspace_ctx *ctx, const pspace_project_args *
 
 /* launches of this library's kernels since the context was created (bench "gpu_launches") */
 long long pspace_cuda_launch_count(const pspace_ctx *ctx);
+/* tuning / test switches.  "force_generic" = 1: use the all-warps cp.async projection kernel even where the
+ * TMA warp-specialised kernel applies (the generic kernel is otherwise used only for operands TMA cannot
+ * address: odd column counts or unaligned bases). */
+int pspace_cuda_set_option(pspace_ctx *ctx, const char *name, int value);
 /* description + FLOP count of the kernel the last project call used */
 int pspace_cuda_last_plan(const pspace_ctx *ctx, char *buf, int buflen);
 

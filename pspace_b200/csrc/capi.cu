@@ -262,6 +262,12 @@ int pspace_cuda_project_matrix_host(pspace_ctx *c, const pspace_project_args *a,
 
 long long pspace_cuda_launch_count(const pspace_ctx *c) { return c ? c->launches : 0; }
 
+int pspace_cuda_set_option(pspace_ctx *c, const char *name, int value) {
+  if (!c || !name) return ps_fail(PSPACE_EINVAL, "null argument");
+  if (!strcmp(name, "force_generic")) { c->force_generic = value; return PSPACE_OK; }
+  return ps_fail(PSPACE_EINVAL, "unknown option %s", name);
+}
+
 int pspace_cuda_last_plan(const pspace_ctx *c, char *buf, int buflen) {
   if (!c || !buf || buflen < 1) return ps_fail(PSPACE_EINVAL, "null argument");
   snprintf(buf, buflen, "%s flop=%.6e", c->plan.c_str(), c->plan_flop);

@@ -26,6 +26,8 @@ struct pspace_ctx {
   double *d_W = nullptr;                 // [Q] scalars
   long long launches = 0;
   std::string plan;
+  const char *plan_kernel = "";
+  int force_generic = 0;                 // tests: force the cp.async kernel even where TMA is usable
   double plan_flop = 0.0;
   // scratch owned by the context for the host-buffer entry points
   void *d_scratch_in = nullptr, *d_scratch_out = nullptr, *d_scratch_ws = nullptr;

@@ -27,6 +27,7 @@
 //    (deterministic — no atomics).
 #include "ctx.h"
 #include <algorithm>
+#include <cuda.h>
 #include <stdio.h>
 
 namespace {
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(NT, TL::MINB) k_project(const __grid_constant_
   constexpr bool CPLX = TL::CPLX;
   constexpr bool MAT = TL::MODE == MODE_MATRIX;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   double *Ts = reinterpret_cast<double *>(smem_raw);                 // (tsz + ZPAD) * W
   double *Bs = Ts + (size_t)(p.tsz + ZPAD) * W;                      // STAGES * KQ * LDB
   if ((((size_t)(p.tsz + ZPAD) * W) & 1) != 0) Bs += 1;              // keep 16-byte alignment (slack is in the size)
@@ -328,6 +329,321 @@ __global__ void __launch_bounds__(NT, TL::MINB) k_project(const __grid_constant_
   }
 }
 
+
+// =====================================================================================================
+// Warp-specialised TMA variant (the fast path; used whenever the right operand is TMA-addressable, i.e.
+// 16-byte aligned base and an even number of real columns).
+//
+//   warps 0-3  (one per SM sub-partition) = PRODUCER warpgroup, setmaxnreg.dec:
+//        thread 0 arms full[s] with expect_tx and issues ONE cp.async.bulk.tensor.2d (TMA) per stage for the
+//        J tile: box = KQ rows x (BN+4) columns — the 4 over-fetched columns are what gives the shared-memory
+//        tile its conflict-free pitch (BN+4 == 4 mod 16 doubles) with a dense TMA box; out-of-range rows /
+//        columns are zero-filled by the TMA unit, which also handles the ragged last chunk.
+//        All 128 threads stage psi_i(q) / w_q psi_j(q) of that chunk into the same stage (lane = quadrature
+//        point, warp = basis-row group) from the shared-memory 1-D tables and the digits of q.
+//   warps 4-11 (two per sub-partition) = CONSUMER warpgroups, setmaxnreg.inc:
+//        wait full[s], build A fragments with one DMUL each, issue DMMA.8x8x4, release empty[s].
+// full[s]/empty[s] are mbarriers; the ring has TL::STAGES stages.
+// =====================================================================================================
+constexpr int NT_WS = 384;
+constexpr int NPROD = 128;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, unsigned long long *bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+               ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+template <class TL> struct WsLayout {
+  static constexpr int W = TL::W;
+  static constexpr int B_BYTES = KQ * TL::LDB * 8;
+  static constexpr int PJ_BYTES = W * KQ * TL::PJP * 8;
+  static constexpr int PI_BYTES = (TL::MODE == MODE_MATRIX) ? W * KQ * TL::BIP * 8 : 0;
+  static constexpr int STAGE_BYTES = ((B_BYTES + PJ_BYTES + PI_BYTES + 127) / 128) * 128;
+  static constexpr int FIT = (192 * 1024) / STAGE_BYTES;          // leave >= 35 KB for tables / row offsets
+  static constexpr int STAGES = FIT > 6 ? 6 : (FIT < 2 ? 2 : FIT);
+  static size_t smem_bytes(int tsz, int nvars) {
+    size_t b = (size_t)STAGES * STAGE_BYTES + 2 * STAGES * 8 + 64;
+    b += (size_t)(tsz + ZPAD) * W * 8 + 16;
+    b += (size_t)TL::NE * nvars * 2 + 16;
+    b += (size_t)NPROD * 32;
+    return (b + 127) & ~(size_t)127;
+  }
+};
+
+template <class TL>
+__global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__ ProjParams p,
+                                                         const __grid_constant__ CUtensorMap tmap) {
+  constexpr int WM = TL::WM, WN = TL::WN, WGN = TL::WGN, W = TL::W, BN = TL::BN, BI = TL::BI;
+  typedef WsLayout<TL> LY;
+  constexpr int LDB = TL::LDB, BIP = TL::BIP, PJP = TL::PJP, NE = TL::NE, STAGES = LY::STAGES;
+  constexpr bool CPLX = TL::CPLX;
+  constexpr bool MAT = TL::MODE == MODE_MATRIX;
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char *stage_base = smem_raw;
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)STAGES * LY::STAGE_BYTES);
+  unsigned long long *empty = full + STAGES;
+  double *Ts = reinterpret_cast<double *>(empty + STAGES);                          // 16-B aligned (STAGES*16 bytes of barriers)
+  unsigned short *eoff = reinterpret_cast<unsigned short *>(Ts + (size_t)(p.tsz + ZPAD) * W);
+  unsigned char *digs = reinterpret_cast<unsigned char *>((reinterpret_cast<size_t>(eoff + (size_t)NE * p.nvars) + 15) & ~(size_t)15);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  int t = blockIdx.x;
+  const int tn = t % p.tiles_n; t /= p.tiles_n;
+  const int tj = t % p.tiles_j; t /= p.tiles_j;
+  const int ti = t;
+  const int ibase = p.i0 + ti * BI;
+  const int jbase = p.j0 + tj * TL::NJ;
+  const int iend = p.i0 + p.ni, jend = p.j0 + p.nj;
+  const int col0 = tn * BN;
+
+  const long long nchunk_all = (p.q1 - p.q0 + KQ - 1) / KQ;
+  const long long c_begin = blockIdx.y * p.chunks_per_slice;
+  const long long c_end = min(nchunk_all, c_begin + p.chunks_per_slice);
+  const int nchunk = (int)max(0LL, c_end - c_begin);
+
+  // ---- one-time setup (all 12 warps) ---------------------------------------------------------------
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1 + NPROD / 32); mbar_init(&empty[s], (NT_WS - NPROD) / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmap) : "memory");
+  }
+  for (int i = tid; i < p.tsz * W; i += NT_WS) Ts[i] = p.T[i];
+  for (int i = tid; i < ZPAD * W; i += NT_WS) Ts[p.tsz * W + i] = 0.0;
+  for (int e = tid; e < NE * p.nvars; e += NT_WS) {
+    const int r = e / p.nvars, d = e % p.nvars;
+    int k;
+    bool ok;
+    if (MAT) {
+      if (r < BI) { k = ibase + r; ok = k < iend; }
+      else { k = jbase + (r - BI); ok = k < jend; }
+    } else { k = jbase + r; ok = k < jend; }
+    int off = ok ? p.toff[d] + p.deg[(size_t)k * p.nvars + d] * p.nq[d] : (d == 0 ? p.tsz : p.toff[d]);
+    eoff[e] = (unsigned short)off;
+  }
+  __syncthreads();
+
+  if (warp < NPROD / 32) {
+    // =========================== PRODUCER warpgroup ===================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(64));
+    unsigned char *mydig = digs + tid * 32;
+    uint4 dg0 = make_uint4(0, 0, 0, 0), dg1 = make_uint4(0, 0, 0, 0);
+    double wre = 0.0, wim = 0.0;
+    auto fetch_point = [&](int c) {
+      if (c < nchunk) {
+        long long q = p.q0 + (c_begin + c) * KQ + lane;
+        const bool ok = q < p.q1;
+        if (!ok) q = p.q1 - 1;
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.qdig + q * p.DP);
+        dg0 = __ldg(src);
+        if (p.DP == 32) dg1 = __ldg(src + 1);
+        if (CPLX) { wre = ok ? __ldg(p.W + 2 * q) : 0.0; wim = ok ? __ldg(p.W + 2 * q + 1) : 0.0; }
+        else wre = ok ? __ldg(p.W + q) : 0.0;
+      }
+    };
+    fetch_point(0);
+    for (int c = 0; c < nchunk; c++) {
+      const int s = c % STAGES;
+      const unsigned n = (unsigned)(c / STAGES);
+      mbar_wait(&empty[s], (n & 1u) ^ 1u);
+      unsigned char *st = stage_base + (size_t)s * LY::STAGE_BYTES;
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&full[s], (unsigned)LY::B_BYTES);
+        tma_load_2d(st, &tmap, &full[s], col0, (int)((c_begin + c) * KQ));
+      }
+      double *pj = reinterpret_cast<double *>(st + LY::B_BYTES);
+      double *pi = reinterpret_cast<double *>(st + LY::B_BYTES + LY::PJ_BYTES);
+      *reinterpret_cast<uint4 *>(mydig) = dg0;
+      if (p.DP == 32) *reinterpret_cast<uint4 *>(mydig + 16) = dg1;
+      const double cwre = wre, cwim = wim;
+      fetch_point(c + 1);            // next chunk's digits/weight are in flight while this one is staged
+      constexpr int R = 3;           // rows staged concurrently per thread (independent product chains)
+      for (int e0 = warp; e0 < NE; e0 += (NPROD / 32) * R) {
+        double vr[R], vi[R];
+        const unsigned short *eo[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const int e = e0 + r * (NPROD / 32);
+          eo[r] = eoff + (e < NE ? e : e0) * p.nvars;
+          vr[r] = 1.0; vi[r] = 0.0;
+        }
+        for (int d = 0; d < p.nvars; d++) {
+          const int dig = mydig[d];
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            if (!CPLX) vr[r] *= Ts[eo[r][d] + dig];
+            else {
+              const int o = 2 * (eo[r][d] + dig);
+              const double tr = Ts[o], tm = Ts[o + 1];
+              const double nr = vr[r] * tr - vi[r] * tm, ni = vr[r] * tm + vi[r] * tr;
+              vr[r] = nr; vi[r] = ni;
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const int e = e0 + r * (NPROD / 32);
+          if (e >= NE) continue;
+          const bool weighted = !MAT || e >= BI;
+          if (weighted) {
+            double xr = vr[r], xi = vi[r];
+            if (!CPLX) xr *= cwre;
+            else { const double nr = xr * cwre - xi * cwim, ni = xr * cwim + xi * cwre; xr = nr; xi = ni; }
+            const int row = MAT ? e - BI : e;
+            pj[lane * PJP + row] = xr;
+            if (CPLX) pj[KQ * PJP + lane * PJP + row] = xi;
+          } else {
+            pi[lane * BIP + e] = vr[r];
+            if (CPLX) pi[KQ * BIP + lane * BIP + e] = vi[r];
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+  } else {
+    // =========================== CONSUMER warpgroups ==================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(216));
+    const int cw = warp - NPROD / 32;
+    const int wgm = cw / WGN, wgn = cw % WGN;
+    const int g = lane >> 2, kl = lane & 3;
+    double acc[WM][WN][2];
+#pragma unroll
+    for (int a = 0; a < WM; a++)
+#pragma unroll
+      for (int b = 0; b < WN; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const unsigned sgn = (g & 1) ? 0u : 0x80000000u;
+
+    for (int c = 0; c < nchunk; c++) {
+      const int s = c % STAGES;
+      const unsigned n = (unsigned)(c / STAGES);
+      mbar_wait(&full[s], n & 1u);
+      const unsigned char *st = stage_base + (size_t)s * LY::STAGE_BYTES;
+      const double *bs = reinterpret_cast<const double *>(st) + wgn * WN * 8 + g;
+      const double *pj = reinterpret_cast<const double *>(st + LY::B_BYTES);
+      const double *pi = reinterpret_cast<const double *>(st + LY::B_BYTES + LY::PJ_BYTES);
+#pragma unroll
+      for (int ks = 0; ks < KQ / 4; ks++) {
+        const int k = ks * 4 + kl;
+        double are[WM], aim[WM];
+        if (MAT) {
+          const double ajr = pj[k * PJP + g];
+          const double aji = CPLX ? pj[KQ * PJP + k * PJP + g] : 0.0;
+#pragma unroll
+          for (int a = 0; a < WM; a++) {
+            const double air = pi[k * BIP + wgm * WM + a];
+            if (!CPLX) are[a] = air * ajr;
+            else {
+              const double aii = pi[KQ * BIP + k * BIP + wgm * WM + a];
+              are[a] = air * ajr - aii * aji;
+              aim[a] = air * aji + aii * ajr;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int a = 0; a < WM; a++) {
+            are[a] = pj[k * PJP + (wgm * WM + a) * 8 + g];
+            if (CPLX) aim[a] = pj[KQ * PJP + k * PJP + (wgm * WM + a) * 8 + g];
+          }
+        }
+        double bfr[WN], bsw[WN];
+#pragma unroll
+        for (int b = 0; b < WN; b++) {
+          bfr[b] = bs[k * LDB + b * 8];
+          if (CPLX) bsw[b] = flip_sign(bs[k * LDB + b * 8 + ((g & 1) ? -1 : 1)], sgn);
+        }
+#pragma unroll
+        for (int a = 0; a < WM; a++)
+#pragma unroll
+          for (int b = 0; b < WN; b++) {
+            dmma884(acc[a][b][0], acc[a][b][1], are[a], bfr[b]);
+            if (CPLX) dmma884(acc[a][b][0], acc[a][b][1], aim[a], bsw[b]);
+          }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    // ---- epilogue --------------------------------------------------------------------------------
+    double *outp = p.out + (long long)blockIdx.y * p.slice_stride;
+#pragma unroll
+    for (int a = 0; a < WM; a++) {
+      long long rowoff;
+      bool rok;
+      if (MAT) {
+        const int i = ibase + wgm * WM + a, j = jbase + g;
+        rok = i < iend && j < jend;
+        rowoff = (long long)(i - p.i0) * p.stride_i + (long long)(j - p.j0) * p.stride_j;
+      } else {
+        const int k = jbase + (wgm * WM + a) * 8 + g;
+        rok = k < jend;
+        rowoff = (long long)(k - p.j0) * p.stride_j;
+      }
+      if (!rok) continue;
+#pragma unroll
+      for (int b = 0; b < WN; b++) {
+        const int col = col0 + wgn * WN * 8 + b * 8 + 2 * kl;
+        double *dst = outp + rowoff + col;
+        double v0 = acc[a][b][0], v1 = acc[a][b][1];
+        if (col + 1 < p.ncols_d && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
+          if (p.accumulate) { const double2 o = *reinterpret_cast<double2 *>(dst); v0 += o.x; v1 += o.y; }
+          *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
+        } else {
+          if (col < p.ncols_d) dst[0] = p.accumulate ? dst[0] + v0 : v0;
+          if (col + 1 < p.ncols_d) dst[1] = p.accumulate ? dst[1] + v1 : v1;
+        }
+      }
+    }
+  }
+}
+
+// TMA descriptor of the right operand: 2-D fp64 tensor [nrows][ncols_d], row pitch ld_in, box KQ x (BN+4)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_tmap(CUtensorMap *tm, const double *base, long long nrows, int ncols_d, long long ld_in, int box_cols) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym)
+      return ps_fail(PSPACE_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    fn = (EncodeTiledFn)sym;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)ncols_d, (cuuint64_t)nrows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld_in * 8};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)KQ};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return ps_fail(PSPACE_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return PSPACE_OK;
+}
+
 // sums the ksplit partial windows in slice order (deterministic) into the output
 __global__ void k_reduce_slices(const double *ws, long long slice_stride, int ksplit, double *out, long long n,
                                 int accumulate) {
@@ -355,6 +671,24 @@ struct Plan {
 };
 
 template <class TL> int launch(const pspace_ctx *c, ProjParams &p, dim3 grid, cudaStream_t st) {
+  if (p.vec16 && !c->force_generic) {
+    typedef WsLayout<TL> LY;
+    size_t smem = LY::smem_bytes(c->tsz, c->nvars);
+    if (smem <= 227 * 1024) {
+      CUtensorMap tm;
+      int rc = make_tmap(&tm, p.in, p.q1 - p.q0, p.ncols_d, p.ld_in, TL::LDB);
+      if (rc) return rc;
+      static bool attr_ws = false;
+      if (!attr_ws) {
+        PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_ws = true;
+      }
+      k_project_ws<TL><<<grid, NT_WS, smem, st>>>(p, tm);
+      PS_LAUNCH_CHECK(c);
+      const_cast<pspace_ctx *>(c)->plan_kernel = "tma+mbarrier warp-specialised";
+      return PSPACE_OK;
+    }
+  }
   size_t smem = TL::smem_bytes(c->tsz, c->nvars);
   if (smem > 227 * 1024) return ps_fail(PSPACE_EINVAL, "1-D tables too large for the staged kernel (%zu B shared memory)", smem);
   static bool attr_set = false;   // per instantiation
@@ -364,6 +698,7 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, dim3 grid, cu
   }
   k_project<TL><<<grid, NT, smem, st>>>(p);
   PS_LAUNCH_CHECK(c);
+  const_cast<pspace_ctx *>(c)->plan_kernel = "cp.async all-warps";
   return PSPACE_OK;
 }
 
@@ -527,8 +862,8 @@ int ps_project(const pspace_ctx *c, int is_matrix, const pspace_project_args *a,
   const double rows = is_matrix ? (double)p.ni * p.nj : (double)p.nj;
   mc->plan_flop = 2.0 * rows * (double)ncols_d * (double)(a->q1 - a->q0) * (c->is_complex ? 2.0 : 1.0);
   char buf[256];
-  snprintf(buf, sizeof buf, "%s%s tiles=%dx%dx%d ksplit=%d chunks/slice=%lld stages=4 smem=%zuB", c->is_complex ? "z " : "",
-           v.name, pl.tiles_i, pl.tiles_j, pl.tiles_n, pl.ksplit, pl.chunks_per_slice, (size_t)0);
+  snprintf(buf, sizeof buf, "%s%s [%s] tiles=%dx%dx%d ksplit=%d chunks/slice=%lld", c->is_complex ? "z " : "",
+           v.name, c->plan_kernel, pl.tiles_i, pl.tiles_j, pl.tiles_n, pl.ksplit, pl.chunks_per_slice);
   mc->plan = buf;
   return PSPACE_OK;
 }

@@ -205,6 +205,10 @@ class DeviceContainer:
         check(self.L.pspace_cuda_project_vector_host(self.h, ctypes.byref(a), fn.ctypes.data, on.ctypes.data))
         return out
 
+    def setOption(self, name, value):
+        check(self.L.pspace_cuda_set_option(self.h, name.encode(), int(value)))
+        return self
+
     def launchCount(self):
         return self.L.pspace_cuda_launch_count(self.h)
 

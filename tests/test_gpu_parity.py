@@ -231,6 +231,35 @@ def test_every_tile_variant_matches():
     c.close()
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+def test_tma_and_generic_kernels_agree_with_oracle(cplx):
+    """Both projection kernels (TMA warp-specialised; cp.async all-warps) on the same input, incl. ragged q."""
+    rng = np.random.default_rng(21)
+    ps = [("uniform", -1.0, 2.0, 4), ("normal", 0.5, 0.4, 4), ("exponential", 1.0, 0.3, 3)]
+    o = H.CpuContainer(H.oracle_api(cplx), ps, 0).initialize()     # Q = 100 (not a multiple of 32), N = 100
+    c = _dc(ps, 0, cplx).initialize()
+    for m2 in (24, 64, 576):
+        J = rng.normal(size=(o.Q, m2)).astype(o.dtype)
+        if cplx:
+            J = J + 1j * rng.normal(size=J.shape)
+        Jd = torch.from_numpy(J).cuda()
+        ref = o.project_matrix(J, 5, 31, 90, 100, nthreads=8)
+        c.setOption("force_generic", 0)
+        C1 = c.projectMatrix(Jd, 5, 31, 90, 100).cpu().numpy()
+        assert "tma" in c.lastPlan()
+        c.setOption("force_generic", 1)
+        C2 = c.projectMatrix(Jd, 5, 31, 90, 100).cpu().numpy()
+        assert "cp.async" in c.lastPlan()
+        assert normwise(C1, ref) < TOL and normwise(C2, ref) < TOL
+        refF = o.project_vector(J)
+        c.setOption("force_generic", 0)
+        F1 = c.projectVector(Jd).cpu().numpy()
+        c.setOption("force_generic", 1)
+        F2 = c.projectVector(Jd).cpu().numpy()
+        assert normwise(F1, refF) < TOL and normwise(F2, refF) < TOL
+    c.close()
+
+
 def test_error_paths_are_loud():
     from pspace_b200.cabi import PspaceCudaError
     ps = [("normal", 0.0, 1.0, 2)]
