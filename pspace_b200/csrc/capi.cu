@@ -60,6 +60,7 @@ int pspace_cuda_destroy(pspace_ctx *c) {
   cudaSetDevice(c->device);
   cudaFree(c->d_deg); cudaFree(c->d_zp); cudaFree(c->d_yp); cudaFree(c->d_wp); cudaFree(c->d_T);
   cudaFree(c->d_qdig); cudaFree(c->d_W);
+  cudaFree(c->d_panel);
   cudaFree(c->d_scratch_in); cudaFree(c->d_scratch_out); cudaFree(c->d_scratch_ws);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -97,6 +98,7 @@ int pspace_cuda_initialize_basis(pspace_ctx *c, const int *pmax, void *stream) {
   PS_CUDA(cudaMemcpyAsync(c->h_deg.data(), c->d_deg, sizeof(int) * c->h_deg.size(), cudaMemcpyDeviceToHost, st));
   PS_CUDA(cudaStreamSynchronize(st));
   c->basis_ready = true;
+  c->panel_valid = false;
   return ps_build_tables(c, st);
 }
 
@@ -113,6 +115,7 @@ int pspace_cuda_initialize_quadrature(pspace_ctx *c, const int *nqpts, void *str
   for (int d = 0; d < c->nvars; d++) c->nq[d] = nqpts[d];
   c->Q = Q;
   c->quad_ready = true;
+  c->panel_valid = false;
   int rc = ps_build_tables(c, st);
   if (rc) return rc;
   rc = ps_build_grid(c, st);
@@ -265,6 +268,7 @@ long long pspace_cuda_launch_count(const pspace_ctx *c) { return c ? c->launches
 int pspace_cuda_set_option(pspace_ctx *c, const char *name, int value) {
   if (!c || !name) return ps_fail(PSPACE_EINVAL, "null argument");
   if (!strcmp(name, "force_generic")) { c->force_generic = value; return PSPACE_OK; }
+  if (!strcmp(name, "panel_cache")) { c->panel_cache = value; c->panel_valid = false; return PSPACE_OK; }
   return ps_fail(PSPACE_EINVAL, "unknown option %s", name);
 }
 

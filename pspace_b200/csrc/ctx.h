@@ -27,6 +27,11 @@ struct pspace_ctx {
   long long launches = 0;
   std::string plan;
   const char *plan_kernel = "";
+  void *d_panel = nullptr;               // basis panels of the last project call (see project.cu build_panels)
+  size_t panel_bytes = 0;
+  long long panel_key[7] = {0};
+  bool panel_valid = false;
+  int panel_cache = 1;                   // reuse the panels when the (window, q-range) of a call repeats
   int force_generic = 0;                 // tests: force the cp.async kernel even where TMA is usable
   double plan_flop = 0.0;
   // scratch owned by the context for the host-buffer entry points

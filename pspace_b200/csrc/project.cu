@@ -331,19 +331,27 @@ __global__ void __launch_bounds__(NT, TL::MINB) k_project(const __grid_constant_
 
 
 // =====================================================================================================
-// Warp-specialised TMA variant (the fast path; used whenever the right operand is TMA-addressable, i.e.
+// Fast path: TMA + mbarrier, warp-specialised (used whenever the right operand is TMA-addressable, i.e. a
 // 16-byte aligned base and an even number of real columns).
 //
-//   warps 0-3  (one per SM sub-partition) = PRODUCER warpgroup, setmaxnreg.dec:
-//        thread 0 arms full[s] with expect_tx and issues ONE cp.async.bulk.tensor.2d (TMA) per stage for the
-//        J tile: box = KQ rows x (BN+4) columns — the 4 over-fetched columns are what gives the shared-memory
-//        tile its conflict-free pitch (BN+4 == 4 mod 16 doubles) with a dense TMA box; out-of-range rows /
-//        columns are zero-filled by the TMA unit, which also handles the ragged last chunk.
-//        All 128 threads stage psi_i(q) / w_q psi_j(q) of that chunk into the same stage (lane = quadrature
-//        point, warp = basis-row group) from the shared-memory 1-D tables and the digits of q.
-//   warps 4-11 (two per sub-partition) = CONSUMER warpgroups, setmaxnreg.inc:
-//        wait full[s], build A fragments with one DMUL each, issue DMMA.8x8x4, release empty[s].
-// full[s]/empty[s] are mbarriers; the ring has TL::STAGES stages.
+// Two kernels:
+//  k_psi_panel   writes the basis panels of the call once:  Pi[part][q][i] = psi_i(z_q)   (i in the window)
+//                                                           Pj[part][q][j] = w_q psi_j(z_q)
+//                (q-major, basis row contiguous; part = re/im plane).  Products of the shared-memory 1-D
+//                tables in the reference's order.  (ni+nj) x nq x 8 B — 4.8 GB for cfg5, written at HBM
+//                speed in ~1 ms, i.e. 0.05 % of the projection; the pair products psi_i*psi_j (N^2 x Q) are
+//                never materialised.
+//  k_project_ws  warps 0-7 (two per SM sub-partition) = CONSUMERS (setmaxnreg.inc): wait full[s], build their
+//                A fragments a[(i,j)][q] = Pi[q][i] * Pj[q][j] with ONE DMUL each, issue DMMA.8x8x4, release
+//                empty[s].   warps 8-11 = PRODUCER warpgroup (setmaxnreg.dec): one elected thread arms full[s]
+//                with expect_tx and issues THREE TMA tile loads per stage (cp.async.bulk.tensor): the J tile
+//                (KQ rows x BN+4 columns) and the two panel tiles (KQ x BI+2, KQ x 12).  The over-fetched
+//                columns are what gives each shared-memory tile its bank-conflict-free pitch with a dense
+//                TMA box; out-of-range rows/columns are zero-filled by the TMA unit, which also handles the
+//                ragged last chunk and ragged windows.  The producer executes no FP64 instruction, so the
+//                FP64/DMMA pipe is shared only with the consumers' own fragment DMULs (an earlier version
+//                that formed psi in the producer warps lost 10 % to DMUL-vs-DMMA pipe contention:
+//                profiles/r01_project_ws_b).
 // =====================================================================================================
 constexpr int NT_WS = 384;
 constexpr int NPROD = 128;
@@ -373,30 +381,89 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, 
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
                ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, unsigned long long *bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+               ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 
 template <class TL> struct WsLayout {
   static constexpr int W = TL::W;
   static constexpr int B_BYTES = KQ * TL::LDB * 8;
   static constexpr int PJ_BYTES = W * KQ * TL::PJP * 8;
   static constexpr int PI_BYTES = (TL::MODE == MODE_MATRIX) ? W * KQ * TL::BIP * 8 : 0;
-  static constexpr int STAGE_BYTES = ((B_BYTES + PJ_BYTES + PI_BYTES + 127) / 128) * 128;
-  static constexpr int FIT = (192 * 1024) / STAGE_BYTES;          // leave >= 35 KB for tables / row offsets
+  // every TMA destination must be 128-byte aligned
+  static constexpr int PJ_OFF = ((B_BYTES + 127) / 128) * 128;
+  static constexpr int PI_OFF = ((PJ_OFF + PJ_BYTES + 127) / 128) * 128;
+  static constexpr int STAGE_BYTES = ((PI_OFF + PI_BYTES + 127) / 128) * 128;
+  static constexpr int FIT = (220 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = FIT > 6 ? 6 : (FIT < 2 ? 2 : FIT);
-  static size_t smem_bytes(int tsz, int nvars) {
-    size_t b = (size_t)STAGES * STAGE_BYTES + 2 * STAGES * 8 + 64;
-    b += (size_t)(tsz + ZPAD) * W * 8 + 16;
-    b += (size_t)TL::NE * nvars * 2 + 16;
-    b += (size_t)NPROD * 32;
-    return (b + 127) & ~(size_t)127;
-  }
+  static constexpr unsigned TX_BYTES = B_BYTES + PJ_BYTES + PI_BYTES;
+  static size_t smem_bytes() { return (size_t)STAGES * STAGE_BYTES + 2 * STAGES * 8 + 1024; }
 };
+
+struct PanelParams {
+  int nvars, tsz, DP, width;
+  const double *T;
+  const int *deg;
+  const uint8_t *qdig;
+  const double *W;
+  int toff[PSPACE_MAX_VARS], nq[PSPACE_MAX_VARS];
+  long long q0, q1;
+  int r0, nr, nr_pad;       // basis rows [r0, r0+nr), panel row pitch nr_pad (pad rows are written as zeros)
+  int weighted;
+  double *out;              // [width][q1-q0][nr_pad]
+};
+
+// one warp per quadrature point, lanes over basis rows (coalesced row-contiguous stores)
+template <bool CPLX>
+__global__ void __launch_bounds__(256) k_psi_panel(const __grid_constant__ PanelParams p) {
+  constexpr int W = CPLX ? 2 : 1;
+  extern __shared__ __align__(16) unsigned char psm[];
+  double *Ts = reinterpret_cast<double *>(psm);
+  for (int i = threadIdx.x; i < p.tsz * W; i += blockDim.x) Ts[i] = p.T[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long nq = p.q1 - p.q0;
+  const long long r = blockIdx.x * 8LL + warp;
+  if (r >= nq) return;
+  const long long q = p.q0 + r;
+  const uint8_t *dg = p.qdig + q * p.DP;
+  int base[PSPACE_MAX_VARS];     // table offset of (variable d, digit of q), row 0
+  for (int d = 0; d < p.nvars; d++) base[d] = p.toff[d] + dg[d];
+  double wre = 1.0, wim = 0.0;
+  if (p.weighted) { wre = CPLX ? p.W[2 * q] : p.W[q]; wim = CPLX ? p.W[2 * q + 1] : 0.0; }
+  for (int row = lane; row < p.nr_pad; row += 32) {
+    double vr = 0.0, vi = 0.0;
+    if (row < p.nr) {
+      const int *dk = p.deg + (size_t)(p.r0 + row) * p.nvars;
+      vr = 1.0;
+      for (int d = 0; d < p.nvars; d++) {
+        const int o = base[d] + dk[d] * p.nq[d];
+        if (!CPLX) vr *= Ts[o];
+        else {
+          const double tr = Ts[2 * o], tm = Ts[2 * o + 1];
+          const double nr = vr * tr - vi * tm, ni = vr * tm + vi * tr;
+          vr = nr; vi = ni;
+        }
+      }
+      if (p.weighted) {
+        if (!CPLX) vr *= wre;
+        else { const double nr = vr * wre - vi * wim, ni = vr * wim + vi * wre; vr = nr; vi = ni; }
+      }
+    }
+    p.out[r * p.nr_pad + row] = vr;
+    if (CPLX) p.out[(nq + r) * p.nr_pad + row] = vi;
+  }
+}
 
 template <class TL>
 __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__ ProjParams p,
-                                                         const __grid_constant__ CUtensorMap tmap) {
-  constexpr int WM = TL::WM, WN = TL::WN, WGN = TL::WGN, W = TL::W, BN = TL::BN, BI = TL::BI;
+                                                         const __grid_constant__ CUtensorMap tmapB,
+                                                         const __grid_constant__ CUtensorMap tmapI,
+                                                         const __grid_constant__ CUtensorMap tmapJ) {
   typedef WsLayout<TL> LY;
-  constexpr int LDB = TL::LDB, BIP = TL::BIP, PJP = TL::PJP, NE = TL::NE, STAGES = LY::STAGES;
+  constexpr int WM = TL::WM, WN = TL::WN, WGN = TL::WGN, W = TL::W, BN = TL::BN, BI = TL::BI;
+  constexpr int LDB = TL::LDB, BIP = TL::BIP, PJP = TL::PJP, STAGES = LY::STAGES;
   constexpr bool CPLX = TL::CPLX;
   constexpr bool MAT = TL::MODE == MODE_MATRIX;
 
@@ -404,9 +471,6 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
   unsigned char *stage_base = smem_raw;
   unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)STAGES * LY::STAGE_BYTES);
   unsigned long long *empty = full + STAGES;
-  double *Ts = reinterpret_cast<double *>(empty + STAGES);                          // 16-B aligned (STAGES*16 bytes of barriers)
-  unsigned short *eoff = reinterpret_cast<unsigned short *>(Ts + (size_t)(p.tsz + ZPAD) * W);
-  unsigned char *digs = reinterpret_cast<unsigned char *>((reinterpret_cast<size_t>(eoff + (size_t)NE * p.nvars) + 15) & ~(size_t)15);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -424,150 +488,35 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
   const long long c_end = min(nchunk_all, c_begin + p.chunks_per_slice);
   const int nchunk = (int)max(0LL, c_end - c_begin);
 
-  // ---- one-time setup (all 12 warps) ---------------------------------------------------------------
+  constexpr int NCW = (NT_WS - NPROD) / 32;     // consumer warps 0..7, producer warpgroup = warps 8..11
   if (tid == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1 + NPROD / 32); mbar_init(&empty[s], (NT_WS - NPROD) / 32); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmap) : "memory");
-  }
-  for (int i = tid; i < p.tsz * W; i += NT_WS) Ts[i] = p.T[i];
-  for (int i = tid; i < ZPAD * W; i += NT_WS) Ts[p.tsz * W + i] = 0.0;
-  for (int e = tid; e < NE * p.nvars; e += NT_WS) {
-    const int r = e / p.nvars, d = e % p.nvars;
-    int k;
-    bool ok;
-    if (MAT) {
-      if (r < BI) { k = ibase + r; ok = k < iend; }
-      else { k = jbase + (r - BI); ok = k < jend; }
-    } else { k = jbase + r; ok = k < jend; }
-    int off = ok ? p.toff[d] + p.deg[(size_t)k * p.nvars + d] * p.nq[d] : (d == 0 ? p.tsz : p.toff[d]);
-    eoff[e] = (unsigned short)off;
   }
   __syncthreads();
 
-  constexpr int NCW = (NT_WS - NPROD) / 32;     // consumer warps 0..7; producers are warps 8..11: the SMSP
-  if (warp >= NCW) {                            // arbiter favours the highest warp id, so producers never starve
-    // =========================== PRODUCER warpgroup ===================================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(64));
-    const int pw = warp - NCW, ptid = tid - NCW * 32;
-    unsigned char *mydig = digs + ptid * 32;
-    uint4 dg0 = make_uint4(0, 0, 0, 0), dg1 = make_uint4(0, 0, 0, 0);
-    double wre = 0.0, wim = 0.0;
-    auto fetch_point = [&](int c) {
-      if (c < nchunk) {
-        long long q = p.q0 + (c_begin + c) * KQ + lane;
-        const bool ok = q < p.q1;
-        if (!ok) q = p.q1 - 1;
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.qdig + q * p.DP);
-        dg0 = __ldg(src);
-        if (p.DP == 32) dg1 = __ldg(src + 1);
-        if (CPLX) { wre = ok ? __ldg(p.W + 2 * q) : 0.0; wim = ok ? __ldg(p.W + 2 * q + 1) : 0.0; }
-        else wre = ok ? __ldg(p.W + q) : 0.0;
+  if (warp >= NCW) {
+    // =========================== PRODUCER warpgroup: TMA only =========================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(40));
+    if (tid == NCW * 32) {
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmapB) : "memory");
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmapJ) : "memory");
+      if (MAT) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmapI) : "memory");
+      for (int c = 0; c < nchunk; c++) {
+        const int s = c % STAGES;
+        const unsigned n = (unsigned)(c / STAGES);
+        mbar_wait(&empty[s], (n & 1u) ^ 1u);
+        unsigned char *st = stage_base + (size_t)s * LY::STAGE_BYTES;
+        const int row = (int)((c_begin + c) * KQ);           // quadrature row relative to q0
+        mbar_arrive_expect_tx(&full[s], LY::TX_BYTES);
+        tma_load_2d(st, &tmapB, &full[s], col0, row);
+        tma_load_3d(st + LY::PJ_OFF, &tmapJ, &full[s], jbase - p.j0, row, 0);
+        if (MAT) tma_load_3d(st + LY::PI_OFF, &tmapI, &full[s], ibase - p.i0, row, 0);
       }
-    };
-    constexpr int NPW = NPROD / 32;                 // producer warps
-    constexpr int TR = (NE + NPW - 1) / NPW;        // basis rows owned by one producer warp: e = pw + NPW*t
-    static_assert(TR <= 32, "one lane per owned row in the prefix phase");
-    fetch_point(0);
-    for (int c = 0; c < nchunk; c++) {
-      const int s = c % STAGES;
-      const unsigned n = (unsigned)(c / STAGES);
-      mbar_wait(&empty[s], (n & 1u) ^ 1u);
-      unsigned char *st = stage_base + (size_t)s * LY::STAGE_BYTES;
-      if (ptid == 0) {
-        mbar_arrive_expect_tx(&full[s], (unsigned)LY::B_BYTES);
-        tma_load_2d(st, &tmap, &full[s], col0, (int)((c_begin + c) * KQ));
-      }
-      double *pj = reinterpret_cast<double *>(st + LY::B_BYTES);
-      double *pi = reinterpret_cast<double *>(st + LY::B_BYTES + LY::PJ_BYTES);
-      // leading variables whose digit is the same for all 32 points of the chunk (q is monotone in the lane,
-      // so "same in lane 0 and lane 31" is enough): their table product is formed ONCE per basis row
-      // (lane = row) instead of once per (row, point); the product order stays the reference's
-      // ((1*b_0)*b_1)*...  (ParameterContainer.cpp:184-192).
-      int ncst = 0;
-      {
-        const unsigned w[8] = {dg0.x, dg0.y, dg0.z, dg0.w, dg1.x, dg1.y, dg1.z, dg1.w};
-        bool open = true;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const unsigned diff = __shfl_sync(0xffffffffu, w[i], 0) ^ __shfl_sync(0xffffffffu, w[i], 31);
-          if (open) {
-            if (diff == 0) ncst += 4;
-            else { ncst += (__ffs(diff) - 1) >> 3; open = false; }
-          }
-        }
-        ncst = min(ncst, p.nvars);
-      }
-      *reinterpret_cast<uint4 *>(mydig) = dg0;
-      if (p.DP == 32) *reinterpret_cast<uint4 *>(mydig + 16) = dg1;
-      const double cwre = wre, cwim = wim;
-      fetch_point(c + 1);            // next chunk's digits/weight are in flight while this one is staged
-      __syncwarp();
-      // prefix phase: lane t owns row e = pw + NPW*t
-      double hr = 1.0, hi = 0.0;
-      {
-        const int e = pw + NPW * lane;
-        const unsigned short *eo = eoff + (e < NE ? e : pw) * p.nvars;
-        for (int d = 0; d < ncst; d++) {
-          if (!CPLX) hr *= Ts[eo[d] + mydig[d]];
-          else {
-            const int o = 2 * (eo[d] + mydig[d]);
-            const double tr = Ts[o], tm = Ts[o + 1];
-            const double nr = hr * tr - hi * tm, ni = hr * tm + hi * tr;
-            hr = nr; hi = ni;
-          }
-        }
-      }
-      // point phase: lane = quadrature point; R rows at a time (independent product chains)
-      constexpr int R = 3;
-      for (int t0 = 0; t0 < TR; t0 += R) {
-        double vr[R], vi[R];
-        const unsigned short *eo[R];
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          const int tt = min(t0 + r, TR - 1);
-          const int e = pw + NPW * tt;
-          eo[r] = eoff + (e < NE ? e : pw) * p.nvars;
-          vr[r] = __shfl_sync(0xffffffffu, hr, tt);
-          vi[r] = CPLX ? __shfl_sync(0xffffffffu, hi, tt) : 0.0;
-        }
-        for (int d = ncst; d < p.nvars; d++) {
-          const int dig = mydig[d];
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            if (!CPLX) vr[r] *= Ts[eo[r][d] + dig];
-            else {
-              const int o = 2 * (eo[r][d] + dig);
-              const double tr = Ts[o], tm = Ts[o + 1];
-              const double nr = vr[r] * tr - vi[r] * tm, ni = vr[r] * tm + vi[r] * tr;
-              vr[r] = nr; vi[r] = ni;
-            }
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-          const int e = pw + NPW * (t0 + r);
-          if (t0 + r >= TR || e >= NE) continue;
-          const bool weighted = !MAT || e >= BI;
-          if (weighted) {
-            double xr = vr[r], xi = vi[r];
-            if (!CPLX) xr *= cwre;
-            else { const double nr = xr * cwre - xi * cwim, ni = xr * cwim + xi * cwre; xr = nr; xi = ni; }
-            const int row = MAT ? e - BI : e;
-            pj[lane * PJP + row] = xr;
-            if (CPLX) pj[KQ * PJP + lane * PJP + row] = xi;
-          } else {
-            pi[lane * BIP + e] = vr[r];
-            if (CPLX) pi[KQ * BIP + lane * BIP + e] = vi[r];
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[s]);
     }
   } else {
     // =========================== CONSUMER warpgroups ==================================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(216));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(232));
     const int cw = warp;
     const int wgm = cw / WGN, wgn = cw % WGN;
     const int g = lane >> 2, kl = lane & 3;
@@ -584,8 +533,8 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
       mbar_wait(&full[s], n & 1u);
       const unsigned char *st = stage_base + (size_t)s * LY::STAGE_BYTES;
       const double *bs = reinterpret_cast<const double *>(st) + wgn * WN * 8 + g;
-      const double *pj = reinterpret_cast<const double *>(st + LY::B_BYTES);
-      const double *pi = reinterpret_cast<const double *>(st + LY::B_BYTES + LY::PJ_BYTES);
+      const double *pj = reinterpret_cast<const double *>(st + LY::PJ_OFF);
+      const double *pi = reinterpret_cast<const double *>(st + LY::PI_OFF);
 #pragma unroll
       for (int ks = 0; ks < KQ / 4; ks++) {
         const int k = ks * 4 + kl;
@@ -661,11 +610,12 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
   }
 }
 
-// TMA descriptor of the right operand: 2-D fp64 tensor [nrows][ncols_d], row pitch ld_in, box KQ x (BN+4)
+// TMA descriptors (fp64, no swizzle, zero fill out of bounds).  dims/box innermost first.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int make_tmap(CUtensorMap *tm, const double *base, long long nrows, int ncols_d, long long ld_in, int box_cols) {
+int make_tmap(CUtensorMap *tm, const double *base, int rank, const unsigned long long *dims,
+              const unsigned long long *strides_bytes /*rank-1*/, const unsigned *box) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void *sym = nullptr;
@@ -675,14 +625,63 @@ int make_tmap(CUtensorMap *tm, const double *base, long long nrows, int ncols_d,
       return ps_fail(PSPACE_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
     fn = (EncodeTiledFn)sym;
   }
-  cuuint64_t gdim[2] = {(cuuint64_t)ncols_d, (cuuint64_t)nrows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld_in * 8};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)KQ};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), gdim, gstr, box, estr,
+  cuuint64_t gdim[3], gstr[2];
+  cuuint32_t bx[3], estr[3] = {1, 1, 1};
+  for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, const_cast<double *>(base), gdim, gstr, bx, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return ps_fail(PSPACE_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return PSPACE_OK;
+}
+
+// basis panels of a call, kept in the context (grow-only buffer, reused when the ranges repeat)
+int build_panels(pspace_ctx *c, const ProjParams &p, bool matrix, double **d_pi, double **d_pj, int *ni_pad,
+                 int *nj_pad, cudaStream_t st) {
+  const int W = c->width;
+  const long long nq = p.q1 - p.q0;
+  *ni_pad = matrix ? ((p.ni + 1) & ~1) : 0;
+  *nj_pad = (p.nj + 1) & ~1;
+  const size_t bytes_i = (size_t)W * nq * *ni_pad * 8, bytes_j = (size_t)W * nq * *nj_pad * 8;
+  const size_t off_j = (bytes_i + 255) & ~(size_t)255;
+  const size_t need = off_j + bytes_j;
+  const bool same = c->panel_cache && c->panel_valid && c->panel_key[0] == p.i0 && c->panel_key[1] == p.ni &&
+                    c->panel_key[2] == p.j0 && c->panel_key[3] == p.nj && c->panel_key[4] == p.q0 &&
+                    c->panel_key[5] == p.q1 && c->panel_key[6] == (matrix ? 1 : 0);
+  if (need > c->panel_bytes) {
+    if (c->d_panel) { PS_CUDA(cudaStreamSynchronize(st)); PS_CUDA(cudaFree(c->d_panel)); c->d_panel = nullptr; c->panel_bytes = 0; }
+    cudaError_t e = cudaMalloc(&c->d_panel, need);
+    if (e != cudaSuccess) return ps_fail(PSPACE_ENOMEM, "basis panel of %zu bytes: %s", need, cudaGetErrorString(e));
+    c->panel_bytes = need;
+    c->panel_valid = false;
+  }
+  *d_pi = reinterpret_cast<double *>(c->d_panel);
+  *d_pj = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(c->d_panel) + off_j);
+  if (same && c->panel_valid) return PSPACE_OK;
+  PanelParams pp;
+  pp.nvars = c->nvars; pp.tsz = c->tsz; pp.DP = c->DP; pp.width = W;
+  pp.T = c->d_T; pp.deg = c->d_deg; pp.qdig = c->d_qdig; pp.W = c->d_W;
+  for (int d = 0; d < c->nvars; d++) { pp.toff[d] = c->toff[d]; pp.nq[d] = c->nq[d]; }
+  pp.q0 = p.q0; pp.q1 = p.q1;
+  const size_t smem = (size_t)c->tsz * W * 8;
+  const unsigned nb = (unsigned)((nq + 7) / 8);
+  for (int side = matrix ? 0 : 1; side < 2; side++) {
+    pp.r0 = side ? p.j0 : p.i0; pp.nr = side ? p.nj : p.ni; pp.nr_pad = side ? *nj_pad : *ni_pad;
+    pp.weighted = side; pp.out = side ? *d_pj : *d_pi;
+    if (pp.nr_pad == 0) continue;
+    if (c->is_complex) {
+      PS_CUDA(cudaFuncSetAttribute(k_psi_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_psi_panel<true><<<nb, 256, smem, st>>>(pp);
+    } else {
+      PS_CUDA(cudaFuncSetAttribute(k_psi_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_psi_panel<false><<<nb, 256, smem, st>>>(pp);
+    }
+    PS_LAUNCH_CHECK(c);
+  }
+  c->panel_key[0] = p.i0; c->panel_key[1] = p.ni; c->panel_key[2] = p.j0; c->panel_key[3] = p.nj;
+  c->panel_key[4] = p.q0; c->panel_key[5] = p.q1; c->panel_key[6] = matrix ? 1 : 0;
+  c->panel_valid = true;
   return PSPACE_OK;
 }
 
@@ -713,23 +712,44 @@ struct Plan {
 };
 
 template <class TL> int launch(const pspace_ctx *c, ProjParams &p, dim3 grid, cudaStream_t st) {
+  pspace_ctx *mc = const_cast<pspace_ctx *>(c);
   if (p.vec16 && !c->force_generic) {
     typedef WsLayout<TL> LY;
-    size_t smem = LY::smem_bytes(c->tsz, c->nvars);
-    if (smem <= 227 * 1024) {
-      CUtensorMap tm;
-      int rc = make_tmap(&tm, p.in, p.q1 - p.q0, p.ncols_d, p.ld_in, TL::LDB);
-      if (rc) return rc;
-      static bool attr_ws = false;
-      if (!attr_ws) {
-        PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_ws = true;
-      }
-      k_project_ws<TL><<<grid, NT_WS, smem, st>>>(p, tm);
-      PS_LAUNCH_CHECK(c);
-      const_cast<pspace_ctx *>(c)->plan_kernel = "tma+mbarrier warp-specialised";
-      return PSPACE_OK;
+    constexpr bool MAT = TL::MODE == MODE_MATRIX;
+    const size_t smem = LY::smem_bytes();
+    static_assert(LY::STAGES * LY::STAGE_BYTES + 2048 <= 227 * 1024, "stage ring exceeds shared memory");
+    double *d_pi = nullptr, *d_pj = nullptr;
+    int ni_pad = 0, nj_pad = 0;
+    int rc = build_panels(mc, p, MAT, &d_pi, &d_pj, &ni_pad, &nj_pad, st);
+    if (rc) return rc;
+    const unsigned long long nq = (unsigned long long)(p.q1 - p.q0);
+    CUtensorMap tmB, tmI, tmJ;
+    {
+      unsigned long long dims[2] = {(unsigned long long)p.ncols_d, nq}, str[1] = {(unsigned long long)p.ld_in * 8};
+      unsigned box[2] = {(unsigned)TL::LDB, (unsigned)KQ};
+      if ((rc = make_tmap(&tmB, p.in, 2, dims, str, box))) return rc;
     }
+    {
+      unsigned long long dims[3] = {(unsigned long long)nj_pad, nq, (unsigned long long)TL::W};
+      unsigned long long str[2] = {(unsigned long long)nj_pad * 8, (unsigned long long)nj_pad * 8 * nq};
+      unsigned box[3] = {(unsigned)TL::PJP, (unsigned)KQ, (unsigned)TL::W};
+      if ((rc = make_tmap(&tmJ, d_pj, 3, dims, str, box))) return rc;
+    }
+    if (MAT) {
+      unsigned long long dims[3] = {(unsigned long long)ni_pad, nq, (unsigned long long)TL::W};
+      unsigned long long str[2] = {(unsigned long long)ni_pad * 8, (unsigned long long)ni_pad * 8 * nq};
+      unsigned box[3] = {(unsigned)TL::BIP, (unsigned)KQ, (unsigned)TL::W};
+      if ((rc = make_tmap(&tmI, d_pi, 3, dims, str, box))) return rc;
+    } else tmI = tmJ;
+    static bool attr_ws = false;
+    if (!attr_ws) {
+      PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_ws = true;
+    }
+    k_project_ws<TL><<<grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
+    PS_LAUNCH_CHECK(c);
+    mc->plan_kernel = "tma+mbarrier warp-specialised";
+    return PSPACE_OK;
   }
   size_t smem = TL::smem_bytes(c->tsz, c->nvars);
   if (smem > 227 * 1024) return ps_fail(PSPACE_EINVAL, "1-D tables too large for the staged kernel (%zu B shared memory)", smem);
@@ -740,7 +760,7 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, dim3 grid, cu
   }
   k_project<TL><<<grid, NT, smem, st>>>(p);
   PS_LAUNCH_CHECK(c);
-  const_cast<pspace_ctx *>(c)->plan_kernel = "cp.async all-warps";
+  mc->plan_kernel = "cp.async all-warps";
   return PSPACE_OK;
 }
 
