@@ -130,6 +130,11 @@ int pspace_cuda_project_matrix(const pspace_ctx *ctx, const pspace_project_args 
 int pspace_cuda_project_vector_host(pspace_ctx *ctx, const pspace_project_args *a, const double *h_f, double *h_F);
 int pspace_cuda_project_matrix_host(pspace_ctx *ctx, const pspace_project_args *a, const double *h_J, double *h_C);
 
+/* CUDA-runtime shims so that host code built without CUDA headers can stage buffers (to_device: 1 = H2D, 0 = D2H) */
+int pspace_cuda_malloc(void **p, size_t bytes);
+int pspace_cuda_free(void *p);
+int pspace_cuda_memcpy(void *dst, const void *src, size_t bytes, int to_device);
+
 /* launches of this library's kernels since the context was created (bench "gpu_launches") */
 long long pspace_cuda_launch_count(const pspace_ctx *ctx);
 /* tuning / test switches.  "force_generic" = 1: use the all-warps cp.async projection kernel even where the

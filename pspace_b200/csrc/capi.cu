@@ -263,6 +263,24 @@ int pspace_cuda_project_matrix_host(pspace_ctx *c, const pspace_project_args *a,
   return project_host(c, 1, a, h_J, h_C);
 }
 
+/* CUDA-runtime shims for host code that is compiled without CUDA headers (libpspace.so) */
+int pspace_cuda_malloc(void **p, size_t bytes) {
+  if (!p) return ps_fail(PSPACE_EINVAL, "null argument");
+  *p = nullptr;
+  if (bytes == 0) return PSPACE_OK;
+  PS_CUDA(cudaMalloc(p, bytes));
+  return PSPACE_OK;
+}
+int pspace_cuda_free(void *p) {
+  if (p) PS_CUDA(cudaFree(p));
+  return PSPACE_OK;
+}
+int pspace_cuda_memcpy(void *dst, const void *src, size_t bytes, int to_device) {
+  if (bytes == 0) return PSPACE_OK;
+  PS_CUDA(cudaMemcpy(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
+  return PSPACE_OK;
+}
+
 long long pspace_cuda_launch_count(const pspace_ctx *c) { return c ? c->launches : 0; }
 
 int pspace_cuda_set_option(pspace_ctx *c, const char *name, int value) {

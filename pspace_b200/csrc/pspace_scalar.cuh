@@ -7,10 +7,13 @@
 // No FMA contraction: the translation units that include this for TABLE construction are compiled
 // with -fmad=false so that each product/sum rounds once, like the reference's x86-64 build.
 #pragma once
-#include <cuda_runtime.h>
 #include <math.h>
-
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
 #define PS_HD __host__ __device__ __forceinline__
+#else
+#define PS_HD inline   /* plain host compilers (libpspace.so) instantiate the same formulas */
+#endif
 
 struct cplx {
   double re, im;

@@ -1,0 +1,136 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header declares, the
+host C++ library exports what the reference's wrapper links to, per-parameter host arithmetic against the
+golden vectors, loud failure without a GPU, workload sizes."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests.util import ROOT, golden_params, load_golden, same_bits
+
+LIB = os.path.join(ROOT, "pspace_b200", "lib")
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "pspace_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pspace_cuda_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    import ctypes
+    from pspace_b200 import cabi
+    L = ctypes.CDLL(cabi.LIB_PATH)
+    names = _declared_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), n
+    # the ctypes table covers the header (no undeclared / unbound entry point)
+    assert set(cabi.SIGNATURES) <= set(names)
+    missing = set(names) - set(cabi.SIGNATURES) - {"pspace_cuda_malloc", "pspace_cuda_free", "pspace_cuda_memcpy"}
+    assert not missing, missing
+
+
+def test_cabi_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from pspace_b200 import cabi
+    L = cabi.lib()
+    assert L.pspace_cuda_device_count() < 0
+    import ctypes
+    h = ctypes.c_void_p()
+    kinds = np.zeros(1, dtype=np.intc); p = np.ones(1); d = np.ones(1, dtype=np.intc)
+    rc = L.pspace_cuda_create(ctypes.byref(h), 0, 0, 1, kinds.ctypes.data, p.ctypes.data, p.ctypes.data, d.ctypes.data, 0)
+    assert rc == -2 and b"CUDA" in L.pspace_cuda_last_error()
+    with pytest.raises(cabi.PspaceCudaError):
+        cabi.check(rc)
+
+
+def test_host_container_aborts_without_gpu():
+    """ParameterContainer::initialize() has no CPU path: the process reports and aborts."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from pspace_b200 import PSPACE\n"
+            "ns = PSPACE.bind(False); f = ns.PyParameterFactory(); pc = ns.PyParameterContainer(0)\n"
+            "pc.addParameter(f.createNormalParameter(0.0, 1.0, 2)); pc.initialize(); print('survived')\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode != 0 and "survived" not in r.stdout
+    assert "pspace" in r.stderr and "failed" in r.stderr
+
+
+def test_libpspace_exports_reference_cxx_symbols():
+    """The symbols the reference's compiled wrapper imports (nm -D probe)."""
+    for sub in ("", "complex"):
+        out = subprocess.check_output(["nm", "-DC", os.path.join(LIB, sub, "libpspace.so")], text=True)
+        sc = "std::complex<double>" if sub else "double"
+        for sym in ["ParameterFactory::ParameterFactory()",
+                    f"ParameterFactory::createNormalParameter({sc}, {sc}, int)",
+                    f"ParameterFactory::createUniformParameter({sc}, {sc}, int)",
+                    f"ParameterFactory::createExponentialParameter({sc}, {sc}, int)",
+                    f"ParameterFactory::createNormalParameter({sc}, {sc})",
+                    "ParameterContainer::ParameterContainer(int, int)",
+                    "ParameterContainer::addParameter(AbstractParameter*)",
+                    "ParameterContainer::initialize()",
+                    "ParameterContainer::initializeBasis(int const*)",
+                    "ParameterContainer::initializeQuadrature(int const*)",
+                    f"ParameterContainer::quadrature(int, {sc}*, {sc}*)",
+                    f"ParameterContainer::basis(int, {sc}*)",
+                    "ParameterContainer::getNumBasisTerms()",
+                    "ParameterContainer::getNumParameters()",
+                    "ParameterContainer::getNumQuadraturePoints()",
+                    "ParameterContainer::getBasisParamDeg(int, int*)",
+                    "ParameterContainer::getBasisParamMaxDeg(int*)",
+                    "AbstractParameter::getParameterID()", "AbstractParameter::setMaxDegree(int)"]:
+            assert f" T {sym}" in out, (sub, sym)
+
+
+def _ulps(a, b):
+    a, b = np.asarray(a).view(np.float64), np.asarray(b).view(np.float64)
+    return np.max(np.abs(a - b) / np.maximum(np.spacing(np.abs(b)), 1e-300))
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_host_parameters_against_golden(cplx):
+    """AbstractParameter::quadrature / ::basis on the host (same templates as the device tables)."""
+    from pspace_b200 import PSPACE
+    ns = PSPACE.bind(cplx)
+    g = load_golden("onedim_z" if cplx else "onedim")
+    ps = golden_params(g)
+    f = ns.PyParameterFactory()
+    make = {"normal": f.createNormalParameter, "uniform": f.createUniformParameter, "exponential": f.createExponentialParameter}
+    for pid, (kind, a, b, _) in enumerate(ps):
+        if not cplx:
+            a, b = float(np.real(a)), float(np.real(b))
+        p = make[kind](a, b, 3)
+        for n in range(1, 21):
+            key = f"rule_{pid}_{n}"
+            if key not in g.files:
+                continue
+            got = np.stack(p.quadrature(n))
+            if cplx:
+                assert np.max(np.abs(got - g[key])) <= 1e-15 * np.max(np.abs(g[key])), key
+            else:
+                assert same_bits(got, g[key]), key
+        zs = g[f"z_{pid}"]
+        for d in range(13):
+            got = np.array([p.basis(z, d) for z in zs], dtype=ns.dtype)
+            ref = g[f"poly_{pid}"][d]
+            if cplx:
+                assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref)), (pid, d)
+            elif kind == "uniform" and d >= 5:
+                assert _ulps(got, ref) <= 4, (pid, d)       # double-double integer power vs libm pow
+            else:
+                assert same_bits(got, ref), (pid, d)
+
+
+def test_workload_sizes_match_survey_table():
+    from pspace_b200 import workloads as WL
+    sizes = {k: (f().N, f().Q, f().m) for k, f in WL.ALL.items()}
+    assert sizes == {1: (64, 64, 1), 2: (126, 3125, 8), 3: (1296, 1296, 24), 4: (65536, 65536, 24), 5: (286, 1048576, 24)}
+    assert WL.cfg4().complex_ and WL.cfg5().seed == 20265
