@@ -55,6 +55,7 @@ struct ProjParams {
   int tiles_n, tiles_j, tiles_i;
   long long chunks_per_slice;
   int accumulate, vec16;
+  double *sk_ws;           // stream-K partial tiles: [grid][2][BM*BN]   (fast path only)
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gptr, int src_bytes) {
@@ -473,20 +474,30 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
   unsigned long long *empty = full + STAGES;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  int t = blockIdx.x;
-  const int tn = t % p.tiles_n; t /= p.tiles_n;
-  const int tj = t % p.tiles_j; t /= p.tiles_j;
-  const int ti = t;
-  const int ibase = p.i0 + ti * BI;
-  const int jbase = p.j0 + tj * TL::NJ;
   const int iend = p.i0 + p.ni, jend = p.j0 + p.nj;
-  const int col0 = tn * BN;
 
-  const long long nchunk_all = (p.q1 - p.q0 + KQ - 1) / KQ;
-  const long long c_begin = blockIdx.y * p.chunks_per_slice;
-  const long long c_end = min(nchunk_all, c_begin + p.chunks_per_slice);
-  const int nchunk = (int)max(0LL, c_end - c_begin);
+  // ---- work decomposition: data-parallel full waves + stream-K remainder --------------------------------------
+  // Tiles are numbered tn fastest, then tj, then ti.  With G = gridDim.x persistent CTAs, CTA g owns whole tiles
+  // g, g+G, ... of the first floor(ntiles/G) waves (all q, result stored straight to C), and a contiguous range
+  // [r0,r1) of the remaining rem_tiles*nchunk (tile, chunk) units.  That range is shorter than one tile's
+  // nchunk, so it touches at most two tiles; those partial accumulators go to sk_ws[g][0..1] and k_fixup adds
+  // the pieces of each remainder tile in CTA order (deterministic).  No wave-quantisation tail.
+  const int G = gridDim.x, gcta = blockIdx.x;
+  const int nchunk = (int)((p.q1 - p.q0 + KQ - 1) / KQ);
+  const int ntiles = p.tiles_i * p.tiles_j * p.tiles_n;
+  const int nfull = ntiles / G;
+  const long long rem_units = (long long)(ntiles - nfull * G) * nchunk;
+  const long long r0 = rem_units * gcta / G, r1 = rem_units * (gcta + 1) / G;
+  const int nseg = nfull + (r1 > r0 ? 1 : 0) + ((r1 > r0 && r1 > (r0 / nchunk + 1) * (long long)nchunk) ? 1 : 0);
+  auto segment = [&](int sidx, int &tile, int &c0, int &c1, int &slot) {
+    if (sidx < nfull) { tile = sidx * G + gcta; c0 = 0; c1 = nchunk; slot = -1; return; }
+    const long long ta = r0 / nchunk;
+    if (sidx == nfull) {
+      tile = nfull * G + (int)ta; c0 = (int)(r0 - ta * nchunk); c1 = (int)min((long long)nchunk, r1 - ta * nchunk); slot = 0;
+    } else {
+      tile = nfull * G + (int)ta + 1; c0 = 0; c1 = (int)(r1 - (ta + 1) * nchunk); slot = 1;
+    }
+  };
 
   constexpr int NCW = (NT_WS - NPROD) / 32;     // consumer warps 0..7, producer warpgroup = warps 8..11
   if (tid == 0) {
@@ -502,16 +513,22 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
       asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmapB) : "memory");
       asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmapJ) : "memory");
       if (MAT) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmapI) : "memory");
-      for (int c = 0; c < nchunk; c++) {
-        const int s = c % STAGES;
-        const unsigned n = (unsigned)(c / STAGES);
-        mbar_wait(&empty[s], (n & 1u) ^ 1u);
-        unsigned char *st = stage_base + (size_t)s * LY::STAGE_BYTES;
-        const int row = (int)((c_begin + c) * KQ);           // quadrature row relative to q0
-        mbar_arrive_expect_tx(&full[s], LY::TX_BYTES);
-        tma_load_2d(st, &tmapB, &full[s], col0, row);
-        tma_load_3d(st + LY::PJ_OFF, &tmapJ, &full[s], jbase - p.j0, row, 0);
-        if (MAT) tma_load_3d(st + LY::PI_OFF, &tmapI, &full[s], ibase - p.i0, row, 0);
+      int it = 0;                                     // running chunk counter across segments -> stage / phase
+      for (int sidx = 0; sidx < nseg; sidx++) {
+        int tile, c0, c1, slot;
+        segment(sidx, tile, c0, c1, slot);
+        const int tn = tile % p.tiles_n, tj = (tile / p.tiles_n) % p.tiles_j, ti = tile / (p.tiles_n * p.tiles_j);
+        for (int c = c0; c < c1; c++, it++) {
+          const int s = it % STAGES;
+          const unsigned n = (unsigned)(it / STAGES);
+          mbar_wait(&empty[s], (n & 1u) ^ 1u);
+          unsigned char *st = stage_base + (size_t)s * LY::STAGE_BYTES;
+          const int row = c * KQ;                         // quadrature row relative to q0
+          mbar_arrive_expect_tx(&full[s], LY::TX_BYTES);
+          tma_load_2d(st, &tmapB, &full[s], tn * BN, row);
+          tma_load_3d(st + LY::PJ_OFF, &tmapJ, &full[s], tj * TL::NJ, row, 0);
+          if (MAT) tma_load_3d(st + LY::PI_OFF, &tmapI, &full[s], ti * BI, row, 0);
+        }
       }
     }
   } else {
@@ -520,16 +537,22 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
     const int cw = warp;
     const int wgm = cw / WGN, wgn = cw % WGN;
     const int g = lane >> 2, kl = lane & 3;
+    const unsigned sgn = (g & 1) ? 0u : 0x80000000u;
+    int it = 0;
+    for (int sidx = 0; sidx < nseg; sidx++) {
+    int tile, c0, c1, slot;
+    segment(sidx, tile, c0, c1, slot);
+    const int tn = tile % p.tiles_n, tj = (tile / p.tiles_n) % p.tiles_j, ti = tile / (p.tiles_n * p.tiles_j);
+    const int ibase = p.i0 + ti * BI, jbase = p.j0 + tj * TL::NJ, col0 = tn * BN;
     double acc[WM][WN][2];
 #pragma unroll
     for (int a = 0; a < WM; a++)
 #pragma unroll
       for (int b = 0; b < WN; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-    const unsigned sgn = (g & 1) ? 0u : 0x80000000u;
 
-    for (int c = 0; c < nchunk; c++) {
-      const int s = c % STAGES;
-      const unsigned n = (unsigned)(c / STAGES);
+    for (int c = c0; c < c1; c++, it++) {
+      const int s = it % STAGES;
+      const unsigned n = (unsigned)(it / STAGES);
       mbar_wait(&full[s], n & 1u);
       const unsigned char *st = stage_base + (size_t)s * LY::STAGE_BYTES;
       const double *bs = reinterpret_cast<const double *>(st) + wgn * WN * 8 + g;
@@ -577,8 +600,18 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
       if (lane == 0) mbar_arrive(&empty[s]);
     }
 
-    // ---- epilogue --------------------------------------------------------------------------------
-    double *outp = p.out + (long long)blockIdx.y * p.slice_stride;
+    // ---- epilogue of this segment ----------------------------------------------------------------
+    if (slot >= 0) {
+      // partial tile -> stream-K workspace, dense [BM][BN], no guards (k_fixup applies them)
+      double *wsp = p.sk_ws + ((size_t)gcta * 2 + slot) * (TL::BM * BN);
+#pragma unroll
+      for (int a = 0; a < WM; a++)
+#pragma unroll
+        for (int b = 0; b < WN; b++) {
+          const int r = (wgm * WM + a) * 8 + g, cc = wgn * WN * 8 + b * 8 + 2 * kl;
+          *reinterpret_cast<double2 *>(wsp + (size_t)r * BN + cc) = make_double2(acc[a][b][0], acc[a][b][1]);
+        }
+    } else {
 #pragma unroll
     for (int a = 0; a < WM; a++) {
       long long rowoff;
@@ -596,7 +629,7 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
 #pragma unroll
       for (int b = 0; b < WN; b++) {
         const int col = col0 + wgn * WN * 8 + b * 8 + 2 * kl;
-        double *dst = outp + rowoff + col;
+        double *dst = p.out + rowoff + col;
         double v0 = acc[a][b][0], v1 = acc[a][b][1];
         if (col + 1 < p.ncols_d && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
           if (p.accumulate) { const double2 o = *reinterpret_cast<double2 *>(dst); v0 += o.x; v1 += o.y; }
@@ -607,6 +640,54 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
         }
       }
     }
+    }
+    }   // segments
+  }
+}
+
+// Adds the stream-K pieces of each remainder tile in CTA order and stores the tile (guards, accumulate).
+// One block per remainder tile.  Geometry arguments restate k_project_ws's decomposition.
+__global__ void __launch_bounds__(256) k_fixup(const __grid_constant__ ProjParams p, int G, int BM, int BN, int BI, int NJ,
+                                               int matrix) {
+  const int nchunk = (int)((p.q1 - p.q0 + KQ - 1) / KQ);
+  const int ntiles = p.tiles_i * p.tiles_j * p.tiles_n;
+  const int nfull = ntiles / G;
+  const long long rem_units = (long long)(ntiles - nfull * G) * nchunk;
+  const int rt = blockIdx.x, tile = nfull * G + rt;
+  const int tn = tile % p.tiles_n, tj = (tile / p.tiles_n) % p.tiles_j, ti = tile / (p.tiles_n * p.tiles_j);
+  const int ibase = p.i0 + ti * BI, jbase = p.j0 + tj * NJ, col0 = tn * BN;
+  const int iend = p.i0 + p.ni, jend = p.j0 + p.nj;
+  const long long u0 = (long long)rt * nchunk, u1 = u0 + nchunk;
+  // first CTA whose range reaches past u0:  r1_g = rem_units*(g+1)/G > u0
+  int g_lo = (int)((u0 * G) / rem_units);
+  while (g_lo > 0 && rem_units * g_lo / G > u0) g_lo--;
+  while (rem_units * (g_lo + 1) / G <= u0) g_lo++;
+  for (int e = threadIdx.x; e < BM * BN; e += blockDim.x) {
+    const int r = e / BN, cc = e % BN;
+    double sum = 0.0;
+    for (int g = g_lo; g < G; g++) {
+      const long long a0 = rem_units * g / G, a1 = rem_units * (g + 1) / G;
+      if (a0 >= u1) break;
+      if (a1 <= a0) continue;
+      const int slot = (a0 / nchunk == rt) ? 0 : 1;
+      sum += p.sk_ws[((size_t)g * 2 + slot) * ((size_t)BM * BN) + e];
+    }
+    const int col = col0 + cc;
+    if (col >= p.ncols_d) continue;
+    long long rowoff;
+    bool rok;
+    if (matrix) {
+      const int i = ibase + r / 8, j = jbase + (r & 7);
+      rok = i < iend && j < jend;
+      rowoff = (long long)(i - p.i0) * p.stride_i + (long long)(j - p.j0) * p.stride_j;
+    } else {
+      const int k = jbase + r;
+      rok = k < jend;
+      rowoff = (long long)(k - p.j0) * p.stride_j;
+    }
+    if (!rok) continue;
+    double *dst = p.out + rowoff + col;
+    *dst = p.accumulate ? *dst + sum : sum;
   }
 }
 
@@ -707,11 +788,16 @@ struct Plan {
   int variant_idx;
   int tiles_i, tiles_j, tiles_n, ksplit;
   long long chunks_per_slice, nchunk;
-  size_t ws_bytes;
+  size_t ws_bytes;          // what the caller must provide (max over the two kernels' needs)
+  size_t ws_generic, ws_streamk;
+  int sk_grid, sk_rem_tiles;   // fast path: persistent CTAs, tiles left to the stream-K remainder
   long long out_elems;
 };
 
-template <class TL> int launch(const pspace_ctx *c, ProjParams &p, dim3 grid, cudaStream_t st) {
+// Launches one projection with tile configuration TL.  `fast` = TMA warp-specialised persistent kernel
+// (stream-K, writes C directly + k_fixup); otherwise the generic kernel over (tiles, ksplit) + k_reduce_slices.
+template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &pl, const pspace_project_args *a,
+                               double *d_out, void *d_ws, cudaStream_t st) {
   pspace_ctx *mc = const_cast<pspace_ctx *>(c);
   if (p.vec16 && !c->force_generic) {
     typedef WsLayout<TL> LY;
@@ -746,9 +832,16 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, dim3 grid, cu
       PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_ws = true;
     }
-    k_project_ws<TL><<<grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
+    p.out = d_out;
+    p.accumulate = a->accumulate;
+    p.sk_ws = (double *)d_ws;
+    k_project_ws<TL><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
     PS_LAUNCH_CHECK(c);
-    mc->plan_kernel = "tma+mbarrier warp-specialised";
+    if (pl.sk_rem_tiles > 0) {
+      k_fixup<<<pl.sk_rem_tiles, 256, 0, st>>>(p, pl.sk_grid, TL::BM, TL::BN, TL::BI, TL::NJ, MAT ? 1 : 0);
+      PS_LAUNCH_CHECK(c);
+    }
+    mc->plan_kernel = "tma+mbarrier warp-specialised, persistent stream-K";
     return PSPACE_OK;
   }
   size_t smem = TL::smem_bytes(c->tsz, c->nvars);
@@ -758,21 +851,38 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, dim3 grid, cu
     PS_CUDA(cudaFuncSetAttribute(k_project<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  const bool split = pl.ksplit > 1;
+  p.out = split ? (double *)d_ws : d_out;
+  p.slice_stride = split ? pl.out_elems : 0;
+  p.accumulate = split ? 0 : a->accumulate;
+  dim3 grid((unsigned)((long long)pl.tiles_i * pl.tiles_j * pl.tiles_n), (unsigned)pl.ksplit);
   k_project<TL><<<grid, NT, smem, st>>>(p);
   PS_LAUNCH_CHECK(c);
+  if (split) {
+    const long long n = pl.out_elems;
+    const unsigned nb = (unsigned)std::min<long long>((n + 255) / 256, 148LL * 16);
+    k_reduce_slices<<<nb, 256, 0, st>>>((const double *)d_ws, pl.out_elems, pl.ksplit, d_out, n, a->accumulate);
+    PS_LAUNCH_CHECK(c);
+  }
   mc->plan_kernel = "cp.async all-warps";
   return PSPACE_OK;
 }
 
 //                         WM WN WGM WGN cplx   mode         stages minb
-typedef Tile<4, 6, 4, 2, false, MODE_MATRIX, 4, 1> M96;     // 128 pairs x 96 cols   (m*m = 576 = 6 x 96)
-typedef Tile<4, 4, 4, 2, false, MODE_MATRIX, 4, 1> M64;     // 128 x 64              (m*m = 64)
+// "wide-warp" tiles: each consumer warp owns 16 pairs x ALL columns of the CTA tile, so one fragment DMUL feeds
+// WN = 12 (8) DMMAs; measured 2.6 % faster on cfg5 than the 4x2 warp grid of the same CTA tile (ids 5, 6).
+typedef Tile<2, 12, 8, 1, false, MODE_MATRIX, 4, 1> M96;    // 128 pairs x 96 cols   (m*m = 576 = 6 x 96)
+typedef Tile<2, 8, 8, 1, false, MODE_MATRIX, 4, 1> M64;     // 128 x 64              (m*m = 64)
 typedef Tile<4, 2, 8, 1, false, MODE_MATRIX, 4, 1> M16;     // 256 x 16
 typedef Tile<4, 1, 8, 1, false, MODE_MATRIX, 4, 1> M8;      // 256 x 8               (scalar J)
-typedef Tile<4, 6, 4, 2, true, MODE_MATRIX, 4, 1> ZM96;
-typedef Tile<4, 4, 4, 2, true, MODE_MATRIX, 4, 1> ZM64;
+typedef Tile<4, 6, 4, 2, false, MODE_MATRIX, 4, 1> M96G;    // 128 x 96, 4x2 warp grid
+typedef Tile<4, 4, 4, 2, false, MODE_MATRIX, 4, 1> M64G;    // 128 x 64, 4x2 warp grid
+typedef Tile<2, 12, 8, 1, true, MODE_MATRIX, 4, 1> ZM96;
+typedef Tile<2, 8, 8, 1, true, MODE_MATRIX, 4, 1> ZM64;
 typedef Tile<4, 2, 8, 1, true, MODE_MATRIX, 4, 1> ZM16;
 typedef Tile<4, 1, 8, 1, true, MODE_MATRIX, 4, 1> ZM8;
+typedef Tile<4, 6, 4, 2, true, MODE_MATRIX, 4, 1> ZM96G;
+typedef Tile<4, 4, 4, 2, true, MODE_MATRIX, 4, 1> ZM64G;
 typedef Tile<2, 4, 8, 1, false, MODE_VECTOR, 4, 1> V32;     // 128 basis rows x 32 cols
 typedef Tile<2, 1, 8, 1, false, MODE_VECTOR, 4, 1> V8;
 typedef Tile<2, 4, 8, 1, true, MODE_VECTOR, 4, 1> ZV32;
@@ -781,7 +891,9 @@ typedef Tile<2, 1, 8, 1, true, MODE_VECTOR, 4, 1> ZV8;
 const Variant MAT_VARIANTS[] = {{1, M96::BM, M96::BN, M96::BI, 8, 1, "dmma 128x96"},
                                 {2, M64::BM, M64::BN, M64::BI, 8, 1, "dmma 128x64"},
                                 {3, M16::BM, M16::BN, M16::BI, 8, 1, "dmma 256x16"},
-                                {4, M8::BM, M8::BN, M8::BI, 8, 1, "dmma 256x8"}};
+                                {4, M8::BM, M8::BN, M8::BI, 8, 1, "dmma 256x8"},
+                                {5, M96G::BM, M96G::BN, M96G::BI, 8, 1, "dmma 128x96 (4x2 warps)"},
+                                {6, M64G::BM, M64G::BN, M64G::BI, 8, 1, "dmma 128x64 (4x2 warps)"}};
 const Variant VEC_VARIANTS[] = {{1, V32::BM, V32::BN, 0, V32::BM, 1, "dmma vec 128x32"},
                                 {2, V8::BM, V8::BN, 0, V8::BM, 1, "dmma vec 128x8"}};
 
@@ -802,14 +914,15 @@ int make_plan(const pspace_ctx *c, int is_matrix, const pspace_project_args *a, 
   if (is_matrix && (a->j0 < 0 || a->j1 > c->N || a->j1 < a->j0)) return ps_fail(PSPACE_EINVAL, "j range [%d,%d) outside [0,%d)", a->j0, a->j1, c->N);
   const int ncols_d = a->ncols * c->width;
   const Variant *vs = is_matrix ? MAT_VARIANTS : VEC_VARIANTS;
-  const int nv = is_matrix ? 4 : 2;
+  const int nv = is_matrix ? 6 : 2;
+  const int nauto = is_matrix ? 4 : 2;   // variants considered by the automatic choice
   int best = -1;
   if (a->variant > 0) {
     for (int i = 0; i < nv; i++) if (vs[i].id == a->variant) best = i;
     if (best < 0) return ps_fail(PSPACE_EINVAL, "unknown tile variant %d", a->variant);
   } else {
     double bestcost = 0;
-    for (int i = 0; i < nv; i++) {
+    for (int i = 0; i < nauto; i++) {
       // padded work; ties go to the earlier (wider) variant
       double padn = (double)((ncols_d + vs[i].BN - 1) / vs[i].BN) * vs[i].BN;
       double padm;
@@ -845,7 +958,12 @@ int make_plan(const pspace_ctx *c, int is_matrix, const pspace_project_args *a, 
   pl.chunks_per_slice = ks > 0 ? (pl.nchunk + ks - 1) / ks : 0;
   if (pl.chunks_per_slice > 0) ks = (int)((pl.nchunk + pl.chunks_per_slice - 1) / pl.chunks_per_slice);
   pl.ksplit = std::max(1, ks);
-  pl.ws_bytes = pl.ksplit > 1 ? (size_t)pl.ksplit * pl.out_elems * sizeof(double) : 0;
+  pl.ws_generic = pl.ksplit > 1 ? (size_t)pl.ksplit * pl.out_elems * sizeof(double) : 0;
+  // fast path (possible when the real column count is even; the operand's alignment is only known at launch)
+  pl.sk_grid = (int)std::max<long long>(1, std::min<long long>(sm_count(c->device), ntiles * pl.nchunk));
+  pl.sk_rem_tiles = (int)(ntiles % pl.sk_grid);
+  pl.ws_streamk = (ncols_d % 2 == 0 && pl.sk_rem_tiles > 0) ? (size_t)pl.sk_grid * 2 * v.BM * v.BN * sizeof(double) : 0;
+  pl.ws_bytes = std::max(pl.ws_generic, pl.ws_streamk);
   return PSPACE_OK;
 }
 }  // namespace
@@ -889,43 +1007,37 @@ int ps_project(const pspace_ctx *c, int is_matrix, const pspace_project_args *a,
     p.i0 = 0; p.ni = 1; p.j0 = a->k0; p.nj = a->k1 - a->k0;
     p.stride_j = ncols_d; p.stride_i = 0;
   }
-  const bool split = pl.ksplit > 1;
-  p.out = split ? (double *)d_ws : d_out;
-  p.slice_stride = split ? pl.out_elems : 0;
-  p.accumulate = split ? 0 : a->accumulate;
+  p.out = d_out; p.slice_stride = 0; p.accumulate = a->accumulate; p.sk_ws = nullptr;
 
-  dim3 grid((unsigned)((long long)pl.tiles_i * pl.tiles_j * pl.tiles_n), (unsigned)pl.ksplit);
   const Variant &v = (is_matrix ? MAT_VARIANTS : VEC_VARIANTS)[pl.variant_idx];
   const int key = (is_matrix ? 0 : 100) + (c->is_complex ? 10 : 0) + v.id;
   switch (key) {
-    case 1: rc = launch<M96>(c, p, grid, st); break;
-    case 2: rc = launch<M64>(c, p, grid, st); break;
-    case 3: rc = launch<M16>(c, p, grid, st); break;
-    case 4: rc = launch<M8>(c, p, grid, st); break;
-    case 11: rc = launch<ZM96>(c, p, grid, st); break;
-    case 12: rc = launch<ZM64>(c, p, grid, st); break;
-    case 13: rc = launch<ZM16>(c, p, grid, st); break;
-    case 14: rc = launch<ZM8>(c, p, grid, st); break;
-    case 101: rc = launch<V32>(c, p, grid, st); break;
-    case 102: rc = launch<V8>(c, p, grid, st); break;
-    case 111: rc = launch<ZV32>(c, p, grid, st); break;
-    case 112: rc = launch<ZV8>(c, p, grid, st); break;
+    case 1: rc = launch<M96>(c, p, pl, a, d_out, d_ws, st); break;
+    case 2: rc = launch<M64>(c, p, pl, a, d_out, d_ws, st); break;
+    case 3: rc = launch<M16>(c, p, pl, a, d_out, d_ws, st); break;
+    case 4: rc = launch<M8>(c, p, pl, a, d_out, d_ws, st); break;
+    case 5: rc = launch<M96G>(c, p, pl, a, d_out, d_ws, st); break;
+    case 6: rc = launch<M64G>(c, p, pl, a, d_out, d_ws, st); break;
+    case 11: rc = launch<ZM96>(c, p, pl, a, d_out, d_ws, st); break;
+    case 12: rc = launch<ZM64>(c, p, pl, a, d_out, d_ws, st); break;
+    case 13: rc = launch<ZM16>(c, p, pl, a, d_out, d_ws, st); break;
+    case 14: rc = launch<ZM8>(c, p, pl, a, d_out, d_ws, st); break;
+    case 15: rc = launch<ZM96G>(c, p, pl, a, d_out, d_ws, st); break;
+    case 16: rc = launch<ZM64G>(c, p, pl, a, d_out, d_ws, st); break;
+    case 101: rc = launch<V32>(c, p, pl, a, d_out, d_ws, st); break;
+    case 102: rc = launch<V8>(c, p, pl, a, d_out, d_ws, st); break;
+    case 111: rc = launch<ZV32>(c, p, pl, a, d_out, d_ws, st); break;
+    case 112: rc = launch<ZV8>(c, p, pl, a, d_out, d_ws, st); break;
     default: rc = ps_fail(PSPACE_EINVAL, "no kernel for key %d", key);
   }
   if (rc) return rc;
-  if (split) {
-    long long n = pl.out_elems;
-    unsigned nb = (unsigned)std::min<long long>((n + 255) / 256, 148LL * 16);
-    k_reduce_slices<<<nb, 256, 0, st>>>((const double *)d_ws, pl.out_elems, pl.ksplit, d_out, n, a->accumulate);
-    PS_LAUNCH_CHECK(c);
-  }
   // plan record (bench / DESIGN): executed FLOP = 2 * rows * cols * q per real FMA, x2 again for the two
   // DMMA passes of the complex build (= 8 FLOP per complex FMA)
   const double rows = is_matrix ? (double)p.ni * p.nj : (double)p.nj;
   mc->plan_flop = 2.0 * rows * (double)ncols_d * (double)(a->q1 - a->q0) * (c->is_complex ? 2.0 : 1.0);
   char buf[256];
-  snprintf(buf, sizeof buf, "%s%s [%s] tiles=%dx%dx%d ksplit=%d chunks/slice=%lld", c->is_complex ? "z " : "",
-           v.name, c->plan_kernel, pl.tiles_i, pl.tiles_j, pl.tiles_n, pl.ksplit, pl.chunks_per_slice);
+  snprintf(buf, sizeof buf, "%s%s [%s] tiles=%dx%dx%d chunks=%lld ctas=%d streamk_tiles=%d ksplit(generic)=%d", c->is_complex ? "z " : "",
+           v.name, c->plan_kernel, pl.tiles_i, pl.tiles_j, pl.tiles_n, pl.nchunk, pl.sk_grid, pl.sk_rem_tiles, pl.ksplit);
   mc->plan = buf;
   return PSPACE_OK;
 }

@@ -221,7 +221,7 @@ def test_every_tile_variant_matches():
     J = rng.normal(size=(o.Q, 40))
     Jd = torch.from_numpy(J).cuda()
     ref = o.project_matrix(J, 0, 20, 3, 30, nthreads=4)
-    for variant in (1, 2, 3, 4):
+    for variant in (1, 2, 3, 4, 5, 6):
         C = c.projectMatrix(Jd, 0, 20, 3, 30, variant=variant).cpu().numpy()
         assert normwise(C, ref) < TOL, variant
     refF = o.project_vector(J)
