@@ -307,12 +307,12 @@ def run_b200(args):
     except Exception:
         pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_project_ws (DMMA.8x8x4, FP64 sub-pipe of the tensor pipe)",
+                "traffic": traffic, "kernel": "k_project_ws (persistent stream-K, TMA + mbarrier, DMMA.8x8x4 on the tensor pipe's FP64 sub-pipe)",
                 "peak_source": f"measured in this run: FP64 DMMA {peak_dmma:.2f} / DFMA {peak_dfma:.2f} TFLOP/s register-resident loops "
                                "(MEASURED_PEAKS.json has no FP64 figure; bf16 peak does not apply to an FP64 path)",
                 "kernel_ms": kms, "flop_per_launch": flop_launch,
-                "note": "event time spans the 2 panel kernels + the projection kernel of one call; useful FLOP only "
-                        "(fragment DMULs and padded tile rows are not counted)"}
+                "note": "event time spans the whole project call: 2 basis-panel kernels + k_project_ws + k_fixup; useful FLOP "
+                        "only (fragment DMULs and padded tile rows are not counted)"}
 
     cpu = None
     if not args.no_cpu and world == 1:

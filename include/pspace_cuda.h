@@ -130,6 +130,31 @@ int pspace_cuda_project_matrix(const pspace_ctx *ctx, const pspace_project_args 
 int pspace_cuda_project_vector_host(pspace_ctx *ctx, const pspace_project_args *a, const double *h_f, double *h_F);
 int pspace_cuda_project_matrix_host(pspace_ctx *ctx, const pspace_project_args *a, const double *h_J, double *h_C);
 
+/* ---- (f1) polynomial-chaos expansion evaluated at quadrature points -------------------------------------
+ * U[q][c] = sum_{k in [k0,k1)} psi_k(z_q) V[k-k0][c]  for q in [q0,q1);  d_V[(k1-k0)][ncols], d_U[(q1-q0)][ncols]
+ * scalars, row-major.  Replaces getDeterministicStates / getDeterministicAdjoint of the reference caller
+ * (examples/stacs/cpp/TACSStochasticElement.cpp:53-120; pspace/core.py:788-792), which recompute it with N calls
+ * of basis(k,zq) per node inside every (i,j,q) iteration. */
+int pspace_cuda_evaluate_expansion(const pspace_ctx *ctx, int k0, int k1, long long q0, long long q1, int ncols,
+                                   int accumulate, const double *d_V, double *d_U, void *stream);
+
+/* ---- (f2) TACS-interleaved layouts and the basis-pair sparsity filter (pure index work, bit-exact) ---------------
+ * m = nnodes*ndvpn local dofs; stochastic vectors have nsvpn = N*ndvpn variables per node.
+ * scatter_vector: res[n*nsvpn + i*ndvpn + d] (+)= F[i][n*ndvpn + d]        (TACSStochasticElement.cpp:316-322)
+ * gather_vector : V[k][n*ndvpn + d] = v[n*nsvpn + k*ndvpn + d]             (input of getDeterministicStates :84-120)
+ * scatter_matrix: mat[(ni*nsvpn+i*ndvpn+di)*nsdof + nj*nsvpn+j*ndvpn+dj] (+)= C[i][j][(ni*ndvpn+di)*m + nj*ndvpn+dj]
+ *                 with nsdof = N*m                                          (TACSStochasticElement.cpp:417-432)
+ * point_quantity_layout: out[d*N + i] = F[i][d]                             (TACSStochasticElement.cpp:525)
+ * pair_mask: d_mask[i*N+j] = prod_d (|deg_i[d]-deg_j[d]| <= dmapf[d])       (nonzero(), TACSStochasticElement.cpp:7-21;
+ *            BasisHelper::sparse, BasisHelper.cpp:76-88).  dmapf is a host array of nvars ints. */
+int pspace_cuda_scatter_vector_tacs(int N, int nnodes, int ndvpn, int is_complex, const double *d_F, double *d_res,
+                                    int accumulate, void *stream);
+int pspace_cuda_gather_vector_tacs(int N, int nnodes, int ndvpn, int is_complex, const double *d_v, double *d_V, void *stream);
+int pspace_cuda_scatter_matrix_tacs(int N, int nnodes, int ndvpn, int is_complex, const double *d_C, double *d_mat,
+                                    int accumulate, void *stream);
+int pspace_cuda_point_quantity_layout(int N, int m, int is_complex, const double *d_F, double *d_out, void *stream);
+int pspace_cuda_pair_mask(const pspace_ctx *ctx, const int *dmapf, unsigned char *d_mask, void *stream);
+
 /* CUDA-runtime shims so that host code built without CUDA headers can stage buffers (to_device: 1 = H2D, 0 = D2H) */
 int pspace_cuda_malloc(void **p, size_t bytes);
 int pspace_cuda_free(void *p);

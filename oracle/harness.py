@@ -48,6 +48,7 @@ class _Api:
             "param_basis": (None, [_vp, _i, _i, _vp, _i, _vp]),
             "project_vector": (None, [_vp, _i, _vp, _i, _i, _vp]),
             "project_matrix": (None, [_vp, _i, _vp, _i, _i, _i, _i, _vp, _i]),
+            "evaluate_expansion": (None, [_vp, _i, _vp, _i, _i, _ll, _ll, _vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(self.lib, prefix + name + suffix)
@@ -169,6 +170,15 @@ class CpuContainer:
         C = np.zeros((i1 - i0, j1 - j0, J.shape[1]), dtype=self.dtype)
         self.api.project_matrix(self.h, J.shape[1], _ptr(J), i0, i1, j0, j1, _ptr(C), nthreads)
         return C
+
+    def evaluate_expansion(self, V, k0=0, k1=None, q0=0, q1=None):
+        """U[q][c] = sum_k psi_k(z_q) V[k][c]  (getDeterministicStates)."""
+        k1 = self.N if k1 is None else k1
+        q1 = self.Q if q1 is None else q1
+        V = np.ascontiguousarray(V, dtype=self.dtype).reshape(k1 - k0, -1)
+        U = np.zeros((q1 - q0, V.shape[1]), dtype=self.dtype)
+        self.api.evaluate_expansion(self.h, V.shape[1], _ptr(V), k0, k1, q0, q1, _ptr(U))
+        return U
 
     def project_matrix_qrange(self, Jslice, q0, q1, i0=0, i1=None, j0=0, j1=None, nthreads=1):
         Jslice = np.ascontiguousarray(Jslice, dtype=self.dtype).reshape(q1 - q0, -1)

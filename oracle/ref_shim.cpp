@@ -126,6 +126,24 @@ void refshim_project_vector(void *hh, int m, const double *f_, int k0, int k1, d
   }
 }
 
+// U[q][c] = sum_k v[k][c]*basis(k,zq), k ascending  (getDeterministicStates, TACSStochasticElement.cpp:84-120)
+void refshim_evaluate_expansion(void *hh, int m, const double *V_, int k0, int k1, long long q0, long long q1, double *U_){
+  RefHandle *h = (RefHandle*)hh;
+  const scalar *V = (const scalar*)V_; scalar *U = (scalar*)U_;
+  int nv = h->nvars;
+  std::vector<scalar> zq(nv), yq(nv);
+  for (long long q = q0; q < q1; q++){
+    h->pc->quadrature((int)q, zq.data(), yq.data());
+    scalar *u = U + (size_t)(q-q0)*m;
+    for (int c = 0; c < m; c++) u[c] = 0.0;
+    for (int k = k0; k < k1; k++){
+      scalar psikz = h->pc->basis(k, zq.data());
+      const scalar *v = V + (size_t)(k-k0)*m;
+      for (int c = 0; c < m; c++) u[c] += v[c]*psikz;
+    }
+  }
+}
+
 // C[(i-i0)][(j-j0)][c] = sum_q (basis(i,zq)*basis(j,zq)*wq) * J[q][c]   (TACSStochasticElement.cpp:380-414)
 // rows i are partitioned over nthreads std::threads (container reads are thread-safe after initialize()).
 static void matrix_rows(RefHandle *h, int m2, const scalar *J, int ia, int ib, int i0, int j0, int j1, scalar *C){

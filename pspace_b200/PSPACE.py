@@ -48,6 +48,7 @@ def _load(complex_):
         "pspace_host_basis_param_deg": (None, [_vp, _i, _vp]),
         "pspace_host_basis_param_max_deg": (None, [_vp, _vp]),
         "pspace_host_eval_basis": (None, [_vp, _i, _vp, _vp]),
+        "pspace_host_evaluate_expansion": (None, [_vp, _i, _vp, _vp]),
         "pspace_host_project_vector": (None, [_vp, _i, _vp, _vp]),
         "pspace_host_project_matrix": (None, [_vp, _i, _vp, _vp]),
         "pspace_host_project_matrix_window": (None, [_vp, _i, _vp, _i, _i, _i, _i, _vp]),
@@ -166,6 +167,12 @@ def bind(complex_=False):
             psi = np.zeros((self.getNumBasisTerms(), zz.shape[0]), dtype=dtype)
             L.pspace_host_eval_basis(self.ptr, zz.shape[0], zz.ctypes.data, psi.ctypes.data)
             return psi
+
+        def evaluateExpansion(self, V):
+            VV = np.ascontiguousarray(V, dtype=dtype).reshape(self.getNumBasisTerms(), -1)
+            U = np.zeros((self.getNumQuadraturePoints(), VV.shape[1]), dtype=dtype)
+            L.pspace_host_evaluate_expansion(self.ptr, VV.shape[1], VV.ctypes.data, U.ctypes.data)
+            return U
 
         def projectVector(self, f):
             ff = np.ascontiguousarray(f, dtype=dtype).reshape(self.getNumQuadraturePoints(), -1)

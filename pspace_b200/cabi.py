@@ -47,6 +47,12 @@ SIGNATURES = {
     "pspace_cuda_tensor_grid": (_i, [_vp, _ll, _ll, _vp, _vp, _vp, _vp]),
     "pspace_cuda_eval_basis_grid": (_i, [_vp, _i, _i, _ll, _ll, _vp, _vp]),
     "pspace_cuda_eval_basis_points": (_i, [_vp, _i, _i, _ll, _vp, _vp, _vp]),
+    "pspace_cuda_evaluate_expansion": (_i, [_vp, _i, _i, _ll, _ll, _i, _i, _vp, _vp, _vp]),
+    "pspace_cuda_scatter_vector_tacs": (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "pspace_cuda_gather_vector_tacs": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
+    "pspace_cuda_scatter_matrix_tacs": (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "pspace_cuda_point_quantity_layout": (_i, [_i, _i, _i, _vp, _vp, _vp]),
+    "pspace_cuda_pair_mask": (_i, [_vp, _vp, _vp, _vp]),
     "pspace_cuda_project_workspace": (_sz, [_vp, _i, ctypes.POINTER(ProjectArgs)]),
     "pspace_cuda_project_vector": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _vp, _sz, _vp]),
     "pspace_cuda_project_matrix": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _vp, _sz, _vp]),

@@ -224,6 +224,14 @@ int pspace_cuda_project_matrix(const pspace_ctx *c, const pspace_project_args *a
   return ps_project(c, 1, a, d_J, d_C, d_ws, ws_bytes, (cudaStream_t)stream);
 }
 
+int pspace_cuda_evaluate_expansion(const pspace_ctx *c, int k0, int k1, long long q0, long long q1, int ncols,
+                                   int accumulate, const double *d_V, double *d_U, void *stream) {
+  if (!c) return ps_fail(PSPACE_EINVAL, "null argument");
+  if ((!d_V && k1 > k0) || (!d_U && q1 > q0)) return ps_fail(PSPACE_EINVAL, "null buffer for a non-empty range");
+  PS_CUDA(cudaSetDevice(c->device));
+  return ps_expand(c, k0, k1, q0, q1, ncols, accumulate, d_V, d_U, (cudaStream_t)stream);
+}
+
 static int ensure(void **buf, size_t *have, size_t need) {
   if (need <= *have) return PSPACE_OK;
   if (*buf) { PS_CUDA(cudaFree(*buf)); *buf = nullptr; *have = 0; }

@@ -66,5 +66,7 @@ int ps_tensor_grid(const pspace_ctx *ctx, long long q0, long long q1, double *d_
 int ps_eval_basis_grid(const pspace_ctx *ctx, int k0, int k1, long long q0, long long q1, double *d_psi, cudaStream_t st);
 int ps_eval_basis_points(const pspace_ctx *ctx, int k0, int k1, long long npts, const double *d_z, double *d_psi, cudaStream_t st);
 size_t ps_project_workspace(const pspace_ctx *ctx, int is_matrix, const pspace_project_args *a);
+int ps_expand(const pspace_ctx *c, int k0, int k1, long long q0, long long q1, int ncols, int accumulate,
+              const double *d_V, double *d_U, cudaStream_t st);
 int ps_project(const pspace_ctx *ctx, int is_matrix, const pspace_project_args *a, const double *d_in, double *d_out,
                void *d_ws, size_t ws_bytes, cudaStream_t st);

@@ -968,6 +968,32 @@ int make_plan(const pspace_ctx *c, int is_matrix, const pspace_project_args *a, 
 }
 }  // namespace
 
+// Unweighted / weighted basis panel of rows [r0, r0+nr) over [q0,q1) in the context's panel buffer (used by
+// expand.cu).  Invalidates the projection panel cache (same buffer).
+int ps_build_panel_rows(pspace_ctx *c, int r0, int nr, long long q0, long long q1, int weighted, double **d_panel,
+                        int *nr_pad, cudaStream_t st) {
+  ProjParams p;
+  p.i0 = 0; p.ni = 0; p.j0 = r0; p.nj = nr; p.q0 = q0; p.q1 = q1;
+  double *d_pi = nullptr, *d_pj = nullptr;
+  int ni_pad = 0;
+  const int saved_cache = c->panel_cache;
+  c->panel_cache = 0;
+  c->panel_valid = false;
+  int rc;
+  if (weighted) rc = build_panels(c, p, false, &d_pi, &d_pj, &ni_pad, nr_pad, st);
+  else {
+    // the i side of build_panels is the unweighted one
+    p.i0 = r0; p.ni = nr; p.j0 = 0; p.nj = 0;
+    int nj_pad = 0;
+    rc = build_panels(c, p, true, &d_pi, &d_pj, nr_pad, &nj_pad, st);
+    d_pj = d_pi;
+  }
+  c->panel_cache = saved_cache;
+  c->panel_valid = false;
+  *d_panel = d_pj;
+  return rc;
+}
+
 size_t ps_project_workspace(const pspace_ctx *c, int is_matrix, const pspace_project_args *a) {
   Plan pl;
   if (make_plan(c, is_matrix, a, pl) != PSPACE_OK) return 0;

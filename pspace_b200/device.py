@@ -135,6 +135,20 @@ class DeviceContainer:
             check(self.L.pspace_cuda_eval_basis_points(self.h, k0, k1, zt.shape[0], zt.data_ptr(), psi.data_ptr(), _stream_ptr()))
         return psi
 
+    def evaluateExpansion(self, V, k0=0, k1=None, q0=0, q1=None, out=None, accumulate=False):
+        """U[q][c] = sum_k psi_k(z_q) V[k][c]: the PC expansion with coefficient rows V (device [k1-k0][m]) evaluated
+        at quadrature points q0..q1-1 (getDeterministicStates, TACSStochasticElement.cpp:84-120)."""
+        k1 = self.N if k1 is None else k1
+        q1 = self.Q if q1 is None else q1
+        assert V.is_cuda and V.dtype == self.t_dtype and V.is_contiguous() and V.shape[0] == k1 - k0
+        m = V.shape[1]
+        if out is None:
+            out = torch.empty((q1 - q0, m), dtype=self.t_dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.L.pspace_cuda_evaluate_expansion(self.h, k0, k1, q0, q1, m, int(accumulate), V.data_ptr(),
+                                                        out.data_ptr(), _stream_ptr()))
+        return out
+
     # ---- projections ---------------------------------------------------------------------------------
     def _args(self, k0, k1, j0, j1, q0, q1, ncols, accumulate, ksplit, variant):
         return ProjectArgs(k0, k1, j0, j1, q0, q1, ncols, int(accumulate), ksplit, variant)

@@ -49,6 +49,9 @@ class ParameterContainer {
   void quadrature(int q, scalar *zq, scalar *yq, scalar *wq);
   // psi[k*npts + p] = basis(k, z + p*nvars), all k; host buffers
   void evalBasis(int npts, const scalar *z, scalar *psi);
+  // U[q*m + c] = sum_k psi_k(z_q) V[k*m + c]: the expansion with coefficient rows V evaluated at every quadrature
+  // point (what getDeterministicStates of the reference caller recomputes per (i,j,q)); host buffers
+  void evaluateExpansion(int m, const scalar *V, scalar *U);
   // F[k*m + c] = sum_q w_q psi_k(z_q) f[q*m + c]                      host buffers, all k, all q
   void projectVector(int m, const scalar *f, scalar *F);
   // C[(i*N + j)*m2 + c] = sum_q w_q psi_i(z_q) psi_j(z_q) J[q*m2 + c]  host buffers, all ordered pairs, all q

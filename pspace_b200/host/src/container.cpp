@@ -169,6 +169,20 @@ void ParameterContainer::evalBasis(int npts, const scalar *z, scalar *psi) {
   pspace_cuda_free(dp);
 }
 
+void ParameterContainer::evaluateExpansion(int m, const scalar *V, scalar *U) {
+  ensureContext();
+  const size_t w = PSPACE_SCALAR_WIDTH;
+  const size_t vb = sizeof(double) * w * (size_t)tnum_basis_terms * m, ub = sizeof(double) * w * (size_t)tnum_quadrature_points * m;
+  void *dv = 0, *du = 0;
+  PS_MUST(pspace_cuda_malloc(&dv, vb));
+  PS_MUST(pspace_cuda_malloc(&du, ub));
+  PS_MUST(pspace_cuda_memcpy(dv, V, vb, 1));
+  PS_MUST(pspace_cuda_evaluate_expansion(ctx, 0, tnum_basis_terms, 0, tnum_quadrature_points, m, 0, (const double *)dv, (double *)du, 0));
+  PS_MUST(pspace_cuda_memcpy(U, du, ub, 0));
+  pspace_cuda_free(dv);
+  pspace_cuda_free(du);
+}
+
 void ParameterContainer::projectVector(int m, const scalar *f, scalar *F) {
   ensureContext();
   pspace_project_args a;

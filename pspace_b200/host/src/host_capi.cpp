@@ -60,6 +60,9 @@ void pspace_host_basis_param_max_deg(void *c, int *pmax) { ((ParameterContainer 
 void pspace_host_eval_basis(void *c, int npts, const double *z, double *psi) {
   ((ParameterContainer *)c)->evalBasis(npts, reinterpret_cast<const scalar *>(z), reinterpret_cast<scalar *>(psi));
 }
+void pspace_host_evaluate_expansion(void *c, int m, const double *V, double *U) {
+  ((ParameterContainer *)c)->evaluateExpansion(m, reinterpret_cast<const scalar *>(V), reinterpret_cast<scalar *>(U));
+}
 void pspace_host_project_vector(void *c, int m, const double *f, double *F) {
   ((ParameterContainer *)c)->projectVector(m, reinterpret_cast<const scalar *>(f), reinterpret_cast<scalar *>(F));
 }

@@ -260,6 +260,67 @@ def test_tma_and_generic_kernels_agree_with_oracle(cplx):
     c.close()
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+def test_expansion_evaluation_vs_oracle(cplx):
+    """(f1) U[q][c] = sum_k psi_k(z_q) V[k][c] (getDeterministicStates), incl. ranges, odd columns, accumulate, and the
+    round trip project(evaluate(V)) == V (orthonormality: exact quadrature of degree <= 2p)."""
+    rng = np.random.default_rng(41 + cplx)
+    ps = [("normal", 0.3 + (1e-30j if cplx else 0), 1.2, 3), ("exponential", 0.0, 0.5, 2), ("uniform", -1.0, 2.0, 4),
+          ("normal", -1.0, 0.4, 2)]
+    o = H.CpuContainer(H.oracle_api(cplx), ps, 0).initialize()      # tensor basis: N = Q = 180
+    c = _dc(ps, 0, cplx).initialize()
+    for m in (1, 3, 8, 24, 33, 70):
+        V = rng.normal(size=(o.N, m)).astype(o.dtype)
+        if cplx:
+            V = V + 1j * rng.normal(size=V.shape)
+        Vd = torch.from_numpy(V).cuda()
+        U = c.evaluateExpansion(Vd)
+        assert normwise(U.cpu().numpy(), o.evaluate_expansion(V)) < TOL, m
+        k0, k1, q0, q1 = 3, 41, 17, 150
+        Uw = c.evaluateExpansion(Vd[k0:k1].contiguous(), k0, k1, q0, q1).cpu().numpy()
+        assert normwise(Uw, o.evaluate_expansion(V[k0:k1], k0, k1, q0, q1)) < TOL
+        U2 = c.evaluateExpansion(Vd, out=U.clone(), accumulate=True)
+        assert normwise(U2.cpu().numpy(), 2 * U.cpu().numpy()) < TOL
+        # projection of the evaluated expansion returns the coefficients
+        back = c.projectVector(U).cpu().numpy()
+        assert normwise(back, V) < 1e-11, m
+    c.close()
+
+
+def test_no_write_outside_the_output_window():
+    """compute-sanitizer is closed on this pool: own bounds check.  The output sits inside a larger buffer of
+    sentinels; every kernel path (TMA stream-K incl. fix-up, generic incl. split reduce, vector) must leave the
+    guard bands untouched."""
+    rng = np.random.default_rng(31)
+    ps = [("uniform", -1.0, 2.0, 3), ("normal", 0.5, 0.4, 3), ("exponential", 1.0, 0.3, 3), ("normal", 0.0, 1.0, 2)]
+    c = _dc(ps, 1, False).initialize()
+    N, Q = c.N, c.Q
+    guard = 4096
+    for m2 in (6, 25, 64, 576):
+        J = torch.from_numpy(rng.normal(size=(Q, m2))).cuda()
+        for (i0, i1, j0, j1) in ((0, N, 0, N), (3, 20, 5, 6), (N - 1, N, 0, N)):
+            n = (i1 - i0) * (j1 - j0) * m2
+            for force in (0, 1):
+                c.setOption("force_generic", force)
+                for ks in (0, 2):
+                    buf = torch.full((n + 2 * guard,), -7.25, dtype=torch.float64, device="cuda")
+                    out = buf[guard:guard + n].view(i1 - i0, j1 - j0, m2)
+                    c.projectMatrix(J, i0, i1, j0, j1, out=out, ksplit=ks)
+                    torch.cuda.synchronize()
+                    assert bool((buf[:guard] == -7.25).all()) and bool((buf[guard + n:] == -7.25).all()), (m2, i0, i1, force, ks)
+                    assert not bool((out == -7.25).any())
+        for (k0, k1) in ((0, N), (7, 9)):
+            n = (k1 - k0) * m2
+            for force in (0, 1):
+                c.setOption("force_generic", force)
+                buf = torch.full((n + 2 * guard,), -7.25, dtype=torch.float64, device="cuda")
+                out = buf[guard:guard + n].view(k1 - k0, m2)
+                c.projectVector(J, k0, k1, out=out)
+                torch.cuda.synchronize()
+                assert bool((buf[:guard] == -7.25).all()) and bool((buf[guard + n:] == -7.25).all())
+    c.close()
+
+
 def test_error_paths_are_loud():
     from pspace_b200.cabi import PspaceCudaError
     ps = [("normal", 0.0, 1.0, 2)]

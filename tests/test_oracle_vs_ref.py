@@ -65,6 +65,9 @@ def test_projection_loops_bit_exact(cplx):
     assert same_bits(co.project_vector(f), cr.project_vector(f))
     assert same_bits(co.project_matrix(J, nthreads=3), cr.project_matrix(J, nthreads=2))
     assert same_bits(co.project_matrix(J, 2, 5, 1, 7), cr.project_matrix(J, 2, 5, 1, 7))
+    V = rng.normal(size=(co.N, m)).astype(co.dtype) * (1 + (0.5j if cplx else 0))
+    assert same_bits(co.evaluate_expansion(V), cr.evaluate_expansion(V))
+    assert same_bits(co.evaluate_expansion(V[1:4], 1, 4, 5, 17), cr.evaluate_expansion(V[1:4], 1, 4, 5, 17))
     # q-range restriction used by the sharded tests: ranges sum to the whole (same order inside a range)
     half = co.Q // 2
     Ca = co.project_matrix_qrange(J[:half], 0, half)
