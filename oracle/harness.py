@@ -194,3 +194,39 @@ def synthetic(n, seed, offset=0):
     out = np.zeros(n, dtype=np.float64)
     oracle_api(False).fill_synthetic(_ptr(out), n, seed, offset)
     return out
+
+
+def tacs_scatter_vector(F, nnodes, ndvpn, res=None):
+    """res[n*nsvpn + i*ndvpn + d] += F[i][n*ndvpn + d]  (reference caller loops, TACSStochasticElement.cpp:316-322)."""
+    F = np.ascontiguousarray(F)
+    N = F.shape[0]
+    width = 2 if np.iscomplexobj(F) else 1
+    res = np.zeros(N * nnodes * ndvpn, dtype=F.dtype) if res is None else res
+    lib = oracle_api(False).lib
+    lib.oracle_scatter_vector_tacs.argtypes = [_i, _i, _i, _i, _vp, _vp]
+    lib.oracle_scatter_vector_tacs(N, nnodes, ndvpn, width, _ptr(F), _ptr(res))
+    return res
+
+
+def tacs_scatter_matrix(C, nnodes, ndvpn, mat=None):
+    """mat[...] += C[i][j] blocks in the stochastic-element layout (TACSStochasticElement.cpp:417-432)."""
+    C = np.ascontiguousarray(C)
+    N = C.shape[0]
+    width = 2 if np.iscomplexobj(C) else 1
+    nsdof = N * nnodes * ndvpn
+    mat = np.zeros((nsdof, nsdof), dtype=C.dtype) if mat is None else mat
+    lib = oracle_api(False).lib
+    lib.oracle_scatter_matrix_tacs.argtypes = [_i, _i, _i, _i, _vp, _vp]
+    lib.oracle_scatter_matrix_tacs(N, nnodes, ndvpn, width, _ptr(C), _ptr(mat))
+    return mat
+
+
+def pair_mask(deg, dmapf):
+    deg = np.ascontiguousarray(deg, dtype=np.intc)
+    dm = np.ascontiguousarray(dmapf, dtype=np.intc)
+    N, nv = deg.shape
+    mask = np.zeros((N, N), dtype=np.uint8)
+    lib = oracle_api(False).lib
+    lib.oracle_pair_mask.argtypes = [_i, _i, _vp, _vp, _vp]
+    lib.oracle_pair_mask(N, nv, _ptr(deg), _ptr(dm), _ptr(mask))
+    return mask

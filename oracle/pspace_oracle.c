@@ -30,6 +30,49 @@ void oracle_fill_synthetic(double *out, long long n, unsigned long long seed, un
   }
 }
 
+/* ---- TACS-interleaved layouts (index loops of the reference caller; width = doubles per scalar) ---------------- */
+/* TACSStochasticElement.cpp:316-322: for n, for d: res[n*nsvpn + i*ndvpn + d] += rtmpi[n*ndvpn + d]   (nsvpn = N*ndvpn) */
+void oracle_scatter_vector_tacs(int N, int nnodes, int ndvpn, int width, const double *F, double *res) {
+  const long long nsvpn = (long long)N * ndvpn, m = (long long)nnodes * ndvpn;
+  for (int i = 0; i < N; i++)
+    for (int n = 0; n < nnodes; n++) {
+      const long long lptr = (long long)n * ndvpn, gptr = n * nsvpn + (long long)i * ndvpn;
+      for (int d = 0; d < ndvpn; d++)
+        for (int w = 0; w < width; w++) res[width * (gptr + d) + w] += F[width * (i * m + lptr + d) + w];
+    }
+}
+/* TACSStochasticElement.cpp:417-432: mat[(giptr+di)*nsdof + gjptr+dj] += A[(liptr+di)*nddof + ljptr+dj] */
+void oracle_scatter_matrix_tacs(int N, int nnodes, int ndvpn, int width, const double *C, double *mat) {
+  const long long nsvpn = (long long)N * ndvpn, nddof = (long long)nnodes * ndvpn, nsdof = nddof * N;
+  for (int i = 0; i < N; i++)
+    for (int j = 0; j < N; j++) {
+      const double *A = C + width * (((long long)i * N + j) * nddof * nddof);
+      for (int ni = 0; ni < nnodes; ni++) {
+        const long long liptr = (long long)ni * ndvpn, giptr = ni * nsvpn + (long long)i * ndvpn;
+        for (int di = 0; di < ndvpn; di++)
+          for (int nj = 0; nj < nnodes; nj++) {
+            const long long ljptr = (long long)nj * ndvpn, gjptr = nj * nsvpn + (long long)j * ndvpn;
+            for (int dj = 0; dj < ndvpn; dj++)
+              for (int w = 0; w < width; w++)
+                mat[width * ((giptr + di) * nsdof + gjptr + dj) + w] += A[width * ((liptr + di) * nddof + ljptr + dj) + w];
+          }
+      }
+    }
+}
+/* nonzero(): TACSStochasticElement.cpp:7-21 (BasisHelper::sparse, BasisHelper.cpp:76-88) on a degree table [N][nvars] */
+void oracle_pair_mask(int N, int nvars, const int *deg, const int *dmapf, unsigned char *mask) {
+  for (int i = 0; i < N; i++)
+    for (int j = 0; j < N; j++) {
+      int prod = 1;
+      for (int d = 0; d < nvars; d++) {
+        int diff = deg[i * nvars + d] - deg[j * nvars + d];
+        if (diff < 0) diff = -diff;
+        prod *= (diff <= dmapf[d]) ? 1 : 0;
+      }
+      mask[(long long)i * N + j] = (unsigned char)prod;
+    }
+}
+
 /* ---- real build ---- */
 #define S double
 #define SFX

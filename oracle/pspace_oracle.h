@@ -53,6 +53,10 @@ extern "C" {
 ORACLE_DECL()
 ORACLE_DECL(_z)
 
+void oracle_scatter_vector_tacs(int N, int nnodes, int ndvpn, int width, const double *F, double *res);
+void oracle_scatter_matrix_tacs(int N, int nnodes, int ndvpn, int width, const double *C, double *mat);
+void oracle_pair_mask(int N, int nvars, const int *deg, const int *dmapf, unsigned char *mask);
+
 int oracle_is_complex(void);   /* 0; the _z entry points are the complex build */
 
 /* counter-based synthetic block generator shared (by restating, not linking) with the product bench:

@@ -223,6 +223,15 @@ class DeviceContainer:
         check(self.L.pspace_cuda_set_option(self.h, name.encode(), int(value)))
         return self
 
+    def pairMask(self, dmapf):
+        """mask[i][j] = prod_d(|deg_i[d]-deg_j[d]| <= dmapf[d]) as a device uint8 tensor (nonzero(), TACSStochasticElement.cpp:7-21)."""
+        dm = np.ascontiguousarray(dmapf, dtype=np.intc)
+        assert dm.shape[0] == self.nvars
+        mask = torch.empty((self.N, self.N), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.L.pspace_cuda_pair_mask(self.h, cabi.np_ptr(dm), mask.data_ptr(), _stream_ptr()))
+        return mask
+
     def launchCount(self):
         return self.L.pspace_cuda_launch_count(self.h)
 
@@ -230,6 +239,48 @@ class DeviceContainer:
         buf = ctypes.create_string_buffer(512)
         check(self.L.pspace_cuda_last_plan(self.h, buf, 512))
         return buf.value.decode()
+
+
+# ---- (f2) TACS-interleaved layouts / pair mask -------------------------------------------------------------------
+def _cplx(t):
+    return int(t.is_complex())
+
+
+def scatter_vector_tacs(F, nnodes, ndvpn, res=None, accumulate=True):
+    """res[n*nsvpn + i*ndvpn + d] (+)= F[i][n*ndvpn + d]; F device [N][nnodes*ndvpn]."""
+    N = F.shape[0]
+    assert F.is_cuda and F.is_contiguous() and F.shape[1] == nnodes * ndvpn
+    if res is None:
+        res = torch.zeros(N * nnodes * ndvpn, dtype=F.dtype, device=F.device)
+    check(cabi.lib().pspace_cuda_scatter_vector_tacs(N, nnodes, ndvpn, _cplx(F), F.data_ptr(), res.data_ptr(), int(accumulate), _stream_ptr()))
+    return res
+
+
+def gather_vector_tacs(v, N, nnodes, ndvpn):
+    """V[k][n*ndvpn + d] = v[n*nsvpn + k*ndvpn + d]."""
+    assert v.is_cuda and v.is_contiguous() and v.numel() == N * nnodes * ndvpn
+    V = torch.empty((N, nnodes * ndvpn), dtype=v.dtype, device=v.device)
+    check(cabi.lib().pspace_cuda_gather_vector_tacs(N, nnodes, ndvpn, _cplx(v), v.data_ptr(), V.data_ptr(), _stream_ptr()))
+    return V
+
+
+def scatter_matrix_tacs(C, nnodes, ndvpn, mat=None, accumulate=True):
+    """mat[(ni*nsvpn+i*ndvpn+di)*nsdof + nj*nsvpn+j*ndvpn+dj] (+)= C[i][j][(ni*ndvpn+di)*m + nj*ndvpn+dj]."""
+    N = C.shape[0]
+    m = nnodes * ndvpn
+    assert C.is_cuda and C.is_contiguous() and C.shape[1] == N and C.shape[2] == m * m
+    if mat is None:
+        mat = torch.zeros((N * m, N * m), dtype=C.dtype, device=C.device)
+    check(cabi.lib().pspace_cuda_scatter_matrix_tacs(N, nnodes, ndvpn, _cplx(C), C.data_ptr(), mat.data_ptr(), int(accumulate), _stream_ptr()))
+    return mat
+
+
+def point_quantity_layout(F):
+    """out[d*N + i] = F[i][d]  (evalPointQuantity, TACSStochasticElement.cpp:525)."""
+    N, m = F.shape
+    out = torch.empty(N * m, dtype=F.dtype, device=F.device)
+    check(cabi.lib().pspace_cuda_point_quantity_layout(N, m, _cplx(F), F.data_ptr(), out.data_ptr(), _stream_ptr()))
+    return out
 
 
 def fill_synthetic(n, seed, offset=0, device=0):

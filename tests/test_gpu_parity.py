@@ -287,6 +287,35 @@ def test_expansion_evaluation_vs_oracle(cplx):
     c.close()
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+def test_tacs_layouts_and_pair_mask_bit_exact(cplx):
+    """(f2) interleaved scatter/gather layouts and the sparsity filter: index work, bit-exact vs the oracle loops."""
+    from pspace_b200 import device as D
+    rng = np.random.default_rng(51)
+    ps = [("normal", 0.0, 1.0, 2), ("uniform", 0.0, 1.0, 3), ("exponential", 0.0, 1.0, 1)]
+    o = H.CpuContainer(H.oracle_api(cplx), ps, 1).initialize()
+    c = _dc(ps, 1, cplx).initialize()
+    N = o.N
+    for nnodes, ndvpn in ((1, 1), (2, 3), (3, 2), (4, 6)):
+        m = nnodes * ndvpn
+        F = rng.normal(size=(N, m)).astype(o.dtype) * (1 + (0.3j if cplx else 0))
+        C = rng.normal(size=(N, N, m * m)).astype(o.dtype) * (1 - (0.7j if cplx else 0))
+        res0 = rng.normal(size=N * m).astype(o.dtype)
+        ref = H.tacs_scatter_vector(F, nnodes, ndvpn, res0.copy())
+        got = D.scatter_vector_tacs(torch.from_numpy(F).cuda(), nnodes, ndvpn, torch.from_numpy(res0.copy()).cuda())
+        assert same_bits(got.cpu().numpy(), ref)
+        V = D.gather_vector_tacs(torch.from_numpy(ref).cuda(), N, nnodes, ndvpn).cpu().numpy()
+        assert same_bits(H.tacs_scatter_vector(V, nnodes, ndvpn), ref)          # gather is the inverse permutation
+        refm = H.tacs_scatter_matrix(C, nnodes, ndvpn)
+        gotm = D.scatter_matrix_tacs(torch.from_numpy(C).cuda(), nnodes, ndvpn)
+        assert same_bits(gotm.cpu().numpy(), refm)
+        pq = D.point_quantity_layout(torch.from_numpy(F).cuda()).cpu().numpy()
+        assert same_bits(pq, np.ascontiguousarray(F.T).ravel())
+    for dmapf in ([3, 3, 3], [1, 0, 1], [0, 0, 0], [2, 1, 0]):
+        assert np.array_equal(c.pairMask(dmapf).cpu().numpy(), H.pair_mask(o.degrees(), dmapf)), dmapf
+    c.close()
+
+
 def test_no_write_outside_the_output_window():
     """compute-sanitizer is closed on this pool: own bounds check.  The output sits inside a larger buffer of
     sentinels; every kernel path (TMA stream-K incl. fix-up, generic incl. split reduce, vector) must leave the
