@@ -118,6 +118,10 @@ typedef struct {
   int accumulate;
   int ksplit;               /* 0 = let the library choose; >0 forces the number of q-slices */
   int variant;              /* 0 = auto; otherwise a tile-variant id (bench / tuning) */
+  /* matrix only, optional: DEVICE [N][N] bytes from pspace_cuda_pair_mask (the reference's nonzero() filter,
+   * TACSStochasticElement.cpp:7-21).  Pairs with mask 0 are structurally zero: their blocks are written as 0
+   * (left untouched when accumulate = 1) and tiles without any kept pair are skipped.  NULL = all pairs. */
+  const unsigned char *d_pair_mask;
 } pspace_project_args;
 
 size_t pspace_cuda_project_workspace(const pspace_ctx *ctx, int is_matrix, const pspace_project_args *a);
@@ -154,6 +158,14 @@ int pspace_cuda_scatter_matrix_tacs(int N, int nnodes, int ndvpn, int is_complex
                                     int accumulate, void *stream);
 int pspace_cuda_point_quantity_layout(int N, int m, int is_complex, const double *d_F, double *d_out, void *stream);
 int pspace_cuda_pair_mask(const pspace_ctx *ctx, const int *dmapf, unsigned char *d_mask, void *stream);
+
+/* ---- (f3) moments at the quadrature points -------------------------------------------------------------------
+ * mean[c] = sum_q (w_q psi_0(z_q)) f[q][c],  second[c] = sum_q (w_q psi_0(z_q)) f[q][c]^2,  var = second - mean^2
+ * over q in [q0,q1); d_f[(q1-q0)][ncols] scalars; outputs [ncols] scalars, any may be NULL.  Replaces
+ * TACSStochasticFunction::getFunctionValue (examples/stacs/cpp/TACSStochasticFunction.cpp:209-238).  Sharded
+ * use: combine mean/second across ranks, then var = second - mean^2. */
+int pspace_cuda_moments(const pspace_ctx *ctx, long long q0, long long q1, int ncols, const double *d_f,
+                        double *d_mean, double *d_second, double *d_var, void *stream);
 
 /* CUDA-runtime shims so that host code built without CUDA headers can stage buffers (to_device: 1 = H2D, 0 = D2H) */
 int pspace_cuda_malloc(void **p, size_t bytes);

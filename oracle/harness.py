@@ -55,6 +55,9 @@ class _Api:
             fn.restype, fn.argtypes = res, args
             setattr(self, name, fn)
         if prefix == "oracle_":
+            fn = getattr(self.lib, "oracle_moments" + suffix)
+            fn.restype, fn.argtypes = None, [_vp, _i, _vp, _ll, _ll, _vp, _vp, _vp]
+            self.moments = fn
             fn = getattr(self.lib, "oracle_project_matrix_qrange" + suffix)
             fn.restype, fn.argtypes = None, [_vp, _i, _vp, _i, _i, _i, _i, _ll, _ll, _vp, _i]
             self.project_matrix_qrange = fn
@@ -179,6 +182,13 @@ class CpuContainer:
         U = np.zeros((q1 - q0, V.shape[1]), dtype=self.dtype)
         self.api.evaluate_expansion(self.h, V.shape[1], _ptr(V), k0, k1, q0, q1, _ptr(U))
         return U
+
+    def moments(self, f, q0=0, q1=None):
+        q1 = self.Q if q1 is None else q1
+        f = np.ascontiguousarray(f, dtype=self.dtype).reshape(q1 - q0, -1)
+        out = [np.zeros(f.shape[1], dtype=self.dtype) for _ in range(3)]
+        self.api.moments(self.h, f.shape[1], _ptr(f), q0, q1, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]))
+        return tuple(out)
 
     def project_matrix_qrange(self, Jslice, q0, q1, i0=0, i1=None, j0=0, j1=None, nthreads=1):
         Jslice = np.ascontiguousarray(Jslice, dtype=self.dtype).reshape(q1 - q0, -1)

@@ -44,6 +44,8 @@ extern "C" {
   void oracle_project_vector##SFX(void *h, int m, const double *f, int k0, int k1, double *F);        \
   void oracle_project_matrix##SFX(void *h, int m2, const double *J, int i0, int i1, int j0, int j1,   \
                                   double *C, int nthreads);                                           \
+  void oracle_moments##SFX(void *h, int m, const double *f, long long q0, long long q1, double *mean,   \
+                           double *second, double *var);                                               \
   void oracle_evaluate_expansion##SFX(void *h, int m, const double *V, int k0, int k1, long long q0,    \
                                       long long q1, double *U);                                        \
   /* q-range restricted variants used by the multi-GPU (sharded) parity tests */                      \

@@ -21,7 +21,7 @@ class PspaceCudaError(RuntimeError):
 
 class ProjectArgs(ctypes.Structure):
     _fields_ = [("k0", _i), ("k1", _i), ("j0", _i), ("j1", _i), ("q0", _ll), ("q1", _ll),
-                ("ncols", _i), ("accumulate", _i), ("ksplit", _i), ("variant", _i)]
+                ("ncols", _i), ("accumulate", _i), ("ksplit", _i), ("variant", _i), ("d_pair_mask", _vp)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/pspace_cuda.h
@@ -53,6 +53,7 @@ SIGNATURES = {
     "pspace_cuda_scatter_matrix_tacs": (_i, [_i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "pspace_cuda_point_quantity_layout": (_i, [_i, _i, _i, _vp, _vp, _vp]),
     "pspace_cuda_pair_mask": (_i, [_vp, _vp, _vp, _vp]),
+    "pspace_cuda_moments": (_i, [_vp, _ll, _ll, _i, _vp, _vp, _vp, _vp, _vp]),
     "pspace_cuda_project_workspace": (_sz, [_vp, _i, ctypes.POINTER(ProjectArgs)]),
     "pspace_cuda_project_vector": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _vp, _sz, _vp]),
     "pspace_cuda_project_matrix": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _vp, _sz, _vp]),

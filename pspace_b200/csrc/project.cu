@@ -56,6 +56,10 @@ struct ProjParams {
   long long chunks_per_slice;
   int accumulate, vec16;
   double *sk_ws;           // stream-K partial tiles: [grid][2][BM*BN]   (fast path only)
+  const unsigned char *mask;   // optional basis-pair filter [N][N] (matrix mode): 0 = structurally zero block
+  int mask_ld;                 // = N
+  const int *tile_list;        // fast path with a mask: ids of the tiles that contain at least one kept pair ...
+  const int *tile_count;       // ... and how many there are (device scalars: no host round trip)
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gptr, int src_bytes) {
@@ -304,21 +308,24 @@ __global__ void __launch_bounds__(NT, TL::MINB) k_project(const __grid_constant_
   for (int a = 0; a < WM; a++) {
     long long rowoff;
     bool rok;
+    bool keep = true;
     if (MAT) {
       const int i = ibase + wgm * WM + a, j = jbase + g;
       rok = i < iend && j < jend;
       rowoff = (long long)(i - p.i0) * p.stride_i + (long long)(j - p.j0) * p.stride_j;
+      if (rok && p.mask) keep = p.mask[(size_t)i * p.mask_ld + j] != 0;
     } else {
       const int k = jbase + (wgm * WM + a) * 8 + g;
       rok = k < jend;
       rowoff = (long long)(k - p.j0) * p.stride_j;
     }
     if (!rok) continue;
+    if (!keep && p.accumulate) continue;
 #pragma unroll
     for (int b = 0; b < WN; b++) {
       const int col = col0 + wgn * WN * 8 + b * 8 + 2 * kl;
       double *dst = outp + rowoff + col;
-      double v0 = acc[a][b][0], v1 = acc[a][b][1];
+      double v0 = keep ? acc[a][b][0] : 0.0, v1 = keep ? acc[a][b][1] : 0.0;
       if (col + 1 < p.ncols_d && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
         if (p.accumulate) { const double2 o = *reinterpret_cast<double2 *>(dst); v0 += o.x; v1 += o.y; }
         *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
@@ -484,7 +491,7 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
   // the pieces of each remainder tile in CTA order (deterministic).  No wave-quantisation tail.
   const int G = gridDim.x, gcta = blockIdx.x;
   const int nchunk = (int)((p.q1 - p.q0 + KQ - 1) / KQ);
-  const int ntiles = p.tiles_i * p.tiles_j * p.tiles_n;
+  const int ntiles = p.tile_list ? *p.tile_count : p.tiles_i * p.tiles_j * p.tiles_n;
   const int nfull = ntiles / G;
   const long long rem_units = (long long)(ntiles - nfull * G) * nchunk;
   const long long r0 = rem_units * gcta / G, r1 = rem_units * (gcta + 1) / G;
@@ -497,6 +504,7 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
     } else {
       tile = nfull * G + (int)ta + 1; c0 = 0; c1 = (int)(r1 - (ta + 1) * nchunk); slot = 1;
     }
+    if (p.tile_list) tile = p.tile_list[tile];      // position in the compacted list -> tile id
   };
 
   constexpr int NCW = (NT_WS - NPROD) / 32;     // consumer warps 0..7, producer warpgroup = warps 8..11
@@ -616,21 +624,24 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
     for (int a = 0; a < WM; a++) {
       long long rowoff;
       bool rok;
+      bool keep = true;
       if (MAT) {
         const int i = ibase + wgm * WM + a, j = jbase + g;
         rok = i < iend && j < jend;
         rowoff = (long long)(i - p.i0) * p.stride_i + (long long)(j - p.j0) * p.stride_j;
+        if (rok && p.mask) keep = p.mask[(size_t)i * p.mask_ld + j] != 0;
       } else {
         const int k = jbase + (wgm * WM + a) * 8 + g;
         rok = k < jend;
         rowoff = (long long)(k - p.j0) * p.stride_j;
       }
       if (!rok) continue;
+      if (!keep && p.accumulate) continue;          // filtered pair: contributes nothing
 #pragma unroll
       for (int b = 0; b < WN; b++) {
         const int col = col0 + wgn * WN * 8 + b * 8 + 2 * kl;
         double *dst = p.out + rowoff + col;
-        double v0 = acc[a][b][0], v1 = acc[a][b][1];
+        double v0 = keep ? acc[a][b][0] : 0.0, v1 = keep ? acc[a][b][1] : 0.0;
         if (col + 1 < p.ncols_d && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
           if (p.accumulate) { const double2 o = *reinterpret_cast<double2 *>(dst); v0 += o.x; v1 += o.y; }
           *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
@@ -645,15 +656,55 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
   }
 }
 
+// With a pair mask: ids of the tiles (tn fastest, tj, ti) that hold at least one kept pair, in increasing id order.
+// Single block: the tile count is small (cfg5: 3888) and the order must be reproducible.
+__global__ void __launch_bounds__(256) k_tile_list(const unsigned char *mask, int mask_ld, int i0, int ni, int j0, int nj,
+                                                   int tiles_i, int tiles_j, int tiles_n, int BI, int *list, int *count) {
+  __shared__ int base;
+  __shared__ int wsum[8];
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int npt = tiles_i * tiles_j;                      // pair tiles; each expands to tiles_n column tiles
+  for (int t0 = 0; t0 < npt; t0 += 256) {
+    const int pt = t0 + threadIdx.x;
+    int any = 0;
+    if (pt < npt) {
+      const int ti = pt / tiles_j, tj = pt % tiles_j;
+      for (int a = 0; a < BI && !any; a++) {
+        const int i = i0 + ti * BI + a;
+        if (i >= i0 + ni) break;
+        for (int b = 0; b < 8; b++) {
+          const int j = j0 + tj * 8 + b;
+          if (j < j0 + nj && mask[(size_t)i * mask_ld + j]) { any = 1; break; }
+        }
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, any);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; w++) off += wsum[w];
+    off += __popc(bal & ((1u << lane) - 1));
+    if (any) for (int tn = 0; tn < tiles_n; tn++) list[off * tiles_n + tn] = pt * tiles_n + tn;
+    __syncthreads();
+    if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 8; w++) tot += wsum[w]; base += tot; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base * tiles_n;
+}
+
 // Adds the stream-K pieces of each remainder tile in CTA order and stores the tile (guards, accumulate).
 // One block per remainder tile.  Geometry arguments restate k_project_ws's decomposition.
 __global__ void __launch_bounds__(256) k_fixup(const __grid_constant__ ProjParams p, int G, int BM, int BN, int BI, int NJ,
                                                int matrix) {
   const int nchunk = (int)((p.q1 - p.q0 + KQ - 1) / KQ);
-  const int ntiles = p.tiles_i * p.tiles_j * p.tiles_n;
+  const int ntiles = p.tile_list ? *p.tile_count : p.tiles_i * p.tiles_j * p.tiles_n;
   const int nfull = ntiles / G;
   const long long rem_units = (long long)(ntiles - nfull * G) * nchunk;
-  const int rt = blockIdx.x, tile = nfull * G + rt;
+  const int rt = blockIdx.x;
+  if (rt >= ntiles - nfull * G) return;          // launched with the worst-case G-1 blocks when a tile list is used
+  const int tile = p.tile_list ? p.tile_list[nfull * G + rt] : nfull * G + rt;
   const int tn = tile % p.tiles_n, tj = (tile / p.tiles_n) % p.tiles_j, ti = tile / (p.tiles_n * p.tiles_j);
   const int ibase = p.i0 + ti * BI, jbase = p.j0 + tj * NJ, col0 = tn * BN;
   const int iend = p.i0 + p.ni, jend = p.j0 + p.nj;
@@ -680,6 +731,7 @@ __global__ void __launch_bounds__(256) k_fixup(const __grid_constant__ ProjParam
       const int i = ibase + r / 8, j = jbase + (r & 7);
       rok = i < iend && j < jend;
       rowoff = (long long)(i - p.i0) * p.stride_i + (long long)(j - p.j0) * p.stride_j;
+      if (rok && p.mask && p.mask[(size_t)i * p.mask_ld + j] == 0) { if (p.accumulate) continue; sum = 0.0; }
     } else {
       const int k = jbase + r;
       rok = k < jend;
@@ -835,12 +887,27 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
     p.out = d_out;
     p.accumulate = a->accumulate;
     p.sk_ws = (double *)d_ws;
+    int fix_blocks = pl.sk_rem_tiles;
+    int *d_list = nullptr;
+    if (p.mask) {
+      // tile list on the device; untouched tiles must read as zero
+      const int ntl = p.tiles_i * p.tiles_j * p.tiles_n;
+      PS_CUDA(cudaMallocAsync(&d_list, sizeof(int) * (ntl + 1), st));
+      k_tile_list<<<1, 256, 0, st>>>(p.mask, p.mask_ld, p.i0, p.ni, p.j0, p.nj, p.tiles_i, p.tiles_j, p.tiles_n, TL::BI,
+                                     d_list + 1, d_list);
+      PS_LAUNCH_CHECK(c);
+      p.tile_list = d_list + 1;
+      p.tile_count = d_list;
+      if (!a->accumulate) PS_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * pl.out_elems, st));
+      fix_blocks = pl.sk_grid - 1;     // remainder tile count is only known on the device
+    }
     k_project_ws<TL><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
     PS_LAUNCH_CHECK(c);
-    if (pl.sk_rem_tiles > 0) {
-      k_fixup<<<pl.sk_rem_tiles, 256, 0, st>>>(p, pl.sk_grid, TL::BM, TL::BN, TL::BI, TL::NJ, MAT ? 1 : 0);
+    if (fix_blocks > 0) {
+      k_fixup<<<fix_blocks, 256, 0, st>>>(p, pl.sk_grid, TL::BM, TL::BN, TL::BI, TL::NJ, MAT ? 1 : 0);
       PS_LAUNCH_CHECK(c);
     }
+    if (d_list) PS_CUDA(cudaFreeAsync(d_list, st));
     mc->plan_kernel = "tma+mbarrier warp-specialised, persistent stream-K";
     return PSPACE_OK;
   }
@@ -962,7 +1029,7 @@ int make_plan(const pspace_ctx *c, int is_matrix, const pspace_project_args *a, 
   // fast path (possible when the real column count is even; the operand's alignment is only known at launch)
   pl.sk_grid = (int)std::max<long long>(1, std::min<long long>(sm_count(c->device), ntiles * pl.nchunk));
   pl.sk_rem_tiles = (int)(ntiles % pl.sk_grid);
-  pl.ws_streamk = (ncols_d % 2 == 0 && pl.sk_rem_tiles > 0) ? (size_t)pl.sk_grid * 2 * v.BM * v.BN * sizeof(double) : 0;
+  pl.ws_streamk = (ncols_d % 2 == 0 && (pl.sk_rem_tiles > 0 || (is_matrix && a->d_pair_mask))) ? (size_t)pl.sk_grid * 2 * v.BM * v.BN * sizeof(double) : 0;
   pl.ws_bytes = std::max(pl.ws_generic, pl.ws_streamk);
   return PSPACE_OK;
 }
@@ -1034,6 +1101,7 @@ int ps_project(const pspace_ctx *c, int is_matrix, const pspace_project_args *a,
     p.stride_j = ncols_d; p.stride_i = 0;
   }
   p.out = d_out; p.slice_stride = 0; p.accumulate = a->accumulate; p.sk_ws = nullptr;
+  p.mask = is_matrix ? a->d_pair_mask : nullptr; p.mask_ld = c->N; p.tile_list = nullptr; p.tile_count = nullptr;
 
   const Variant &v = (is_matrix ? MAT_VARIANTS : VEC_VARIANTS)[pl.variant_idx];
   const int key = (is_matrix ? 0 : 100) + (c->is_complex ? 10 : 0) + v.id;

@@ -150,8 +150,9 @@ class DeviceContainer:
         return out
 
     # ---- projections ---------------------------------------------------------------------------------
-    def _args(self, k0, k1, j0, j1, q0, q1, ncols, accumulate, ksplit, variant):
-        return ProjectArgs(k0, k1, j0, j1, q0, q1, ncols, int(accumulate), ksplit, variant)
+    def _args(self, k0, k1, j0, j1, q0, q1, ncols, accumulate, ksplit, variant, mask=None):
+        return ProjectArgs(k0, k1, j0, j1, q0, q1, ncols, int(accumulate), ksplit, variant,
+                           mask.data_ptr() if mask is not None else None)
 
     def _workspace(self, is_matrix, a):
         need = self.L.pspace_cuda_project_workspace(self.h, is_matrix, ctypes.byref(a))
@@ -177,7 +178,7 @@ class DeviceContainer:
         return out
 
     def projectMatrix(self, J, i0=0, i1=None, j0=0, j1=None, q0=0, q1=None, out=None, accumulate=False, ksplit=0,
-                      variant=0):
+                      variant=0, mask=None):
         """C[i][j][c] = sum_q w_q psi_i psi_j J[q][c]; J holds rows q0..q1-1 (device tensor [q1-q0][m2])."""
         i1 = self.N if i1 is None else i1
         j1 = self.N if j1 is None else j1
@@ -186,7 +187,9 @@ class DeviceContainer:
         m2 = J.shape[1]
         if out is None:
             out = torch.empty((i1 - i0, j1 - j0, m2), dtype=self.t_dtype, device=self.device)
-        a = self._args(i0, i1, j0, j1, q0, q1, m2, accumulate, ksplit, variant)
+        if mask is not None:
+            assert mask.is_cuda and mask.dtype == torch.uint8 and mask.shape == (self.N, self.N) and mask.is_contiguous()
+        a = self._args(i0, i1, j0, j1, q0, q1, m2, accumulate, ksplit, variant, mask)
         ws, need = self._workspace(1, a)
         with torch.cuda.device(self.device):
             check(self.L.pspace_cuda_project_matrix(self.h, ctypes.byref(a), J.data_ptr(), out.data_ptr(),
@@ -222,6 +225,17 @@ class DeviceContainer:
     def setOption(self, name, value):
         check(self.L.pspace_cuda_set_option(self.h, name.encode(), int(value)))
         return self
+
+    def moments(self, f, q0=0, q1=None):
+        """(mean, second, variance) over quadrature points of f (device [q1-q0][m]); TACSStochasticFunction.cpp:209-238."""
+        q1 = self.Q if q1 is None else q1
+        assert f.is_cuda and f.dtype == self.t_dtype and f.is_contiguous() and f.shape[0] == q1 - q0
+        m = f.shape[1]
+        out = [torch.empty(m, dtype=self.t_dtype, device=self.device) for _ in range(3)]
+        with torch.cuda.device(self.device):
+            check(self.L.pspace_cuda_moments(self.h, q0, q1, m, f.data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
+                                             out[2].data_ptr(), _stream_ptr()))
+        return tuple(out)
 
     def pairMask(self, dmapf):
         """mask[i][j] = prod_d(|deg_i[d]-deg_j[d]| <= dmapf[d]) as a device uint8 tensor (nonzero(), TACSStochasticElement.cpp:7-21)."""

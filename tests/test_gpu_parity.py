@@ -316,6 +316,74 @@ def test_tacs_layouts_and_pair_mask_bit_exact(cplx):
     c.close()
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+def test_moments_vs_oracle(cplx):
+    """(f3) mean / second moment / variance over the quadrature grid (TACSStochasticFunction.cpp:209-238)."""
+    rng = np.random.default_rng(61)
+    ps = [("normal", 0.3 + (1e-30j if cplx else 0), 1.2, 4), ("exponential", 0.0, 0.5, 3), ("uniform", -1.0, 2.0, 5)]
+    o = H.CpuContainer(H.oracle_api(cplx), ps, 1).initialize()
+    c = _dc(ps, 1, cplx).initialize()
+    for m in (1, 5, 32, 77):
+        f = rng.normal(size=(o.Q, m)).astype(o.dtype) + 2.0
+        if cplx:
+            f = f + 1j * rng.normal(size=f.shape)
+        fd = torch.from_numpy(f).cuda()
+        for (q0, q1) in ((0, o.Q), (7, 93)):
+            ref = o.moments(f[q0:q1], q0, q1)
+            got = c.moments(fd[q0:q1].contiguous(), q0, q1)
+            for g_, r_ in zip(got, ref):
+                assert normwise(g_.cpu().numpy(), r_) < 1e-12, (m, q0)
+    # mean of a PC expansion is its zeroth coefficient, variance the sum of squares of the rest (orthonormal basis)
+    V = rng.normal(size=(o.N, 3)).astype(o.dtype)
+    U = c.evaluateExpansion(torch.from_numpy(V).cuda())
+    mean, _, var = c.moments(U)
+    assert normwise(mean.cpu().numpy(), V[0]) < 1e-11
+    assert normwise(var.cpu().numpy(), (V[1:] * V[1:]).sum(axis=0)) < 1e-10
+    c.close()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_masked_projection_sparsity_filter(cplx):
+    """(f2) projection restricted by the nonzero() pair filter: kept pairs equal the dense result, filtered pairs are
+    exact zeros (or untouched under accumulate); both kernels; J polynomial of degree <= dmapf reproduces the dense
+    projection entirely (that is what the filter is for)."""
+    rng = np.random.default_rng(71)
+    ps = [("normal", 0.2 + (1e-30j if cplx else 0), 0.8, 3), ("uniform", -1.0, 1.5, 3), ("exponential", 0.5, 0.7, 3)]
+    o = H.CpuContainer(H.oracle_api(cplx), ps, 0).initialize()            # N = Q = 64
+    c = _dc(ps, 0, cplx).initialize()
+    N, Q = o.N, o.Q
+    for dmapf in ([1, 1, 1], [0, 2, 1], [3, 3, 3], [0, 0, 0]):
+        maskh = H.pair_mask(o.degrees(), dmapf)
+        mask = c.pairMask(dmapf)
+        for m2 in (4, 64, 9):
+            J = rng.normal(size=(Q, m2)).astype(o.dtype)
+            if cplx:
+                J = J + 1j * rng.normal(size=J.shape)
+            Jd = torch.from_numpy(J).cuda()
+            dense = o.project_matrix(J, nthreads=4)
+            ref = dense * maskh[:, :, None]
+            for force in (0, 1):
+                c.setOption("force_generic", force)
+                got = c.projectMatrix(Jd, mask=mask).cpu().numpy()
+                assert normwise(got, ref) < TOL, (dmapf, m2, force)
+                assert np.all(got[maskh == 0] == 0)
+                base = torch.full((N, N, m2), 3.0, dtype=Jd.dtype, device="cuda")
+                acc = c.projectMatrix(Jd, out=base, accumulate=True, mask=mask).cpu().numpy()
+                assert normwise(acc, ref + 3.0) < TOL
+                assert np.all(acc[maskh == 0] == 3.0)
+                w = c.projectMatrix(Jd, 5, 40, 9, 33, mask=mask).cpu().numpy()
+                assert normwise(w, ref[5:40, 9:33]) < TOL
+            c.setOption("force_generic", 0)
+    # J(y) linear in every y_d: blocks with |deg_i - deg_j| > 1 in some variable vanish, so the filtered projection
+    # with dmapf = 1 equals the dense one
+    _, Y, _ = o.grid()
+    Jlin = (1.0 + Y[:, 0] * 0.5 - Y[:, 1] * 0.25 + Y[:, 2]).reshape(Q, 1) * np.ones((1, 4))
+    dense = o.project_matrix(Jlin.astype(o.dtype), nthreads=4)
+    got = c.projectMatrix(torch.from_numpy(np.ascontiguousarray(Jlin.astype(o.dtype))).cuda(), mask=c.pairMask([1, 1, 1])).cpu().numpy()
+    assert np.max(np.abs(got - dense)) < 1e-12 * np.max(np.abs(dense))
+    c.close()
+
+
 def test_no_write_outside_the_output_window():
     """compute-sanitizer is closed on this pool: own bounds check.  The output sits inside a larger buffer of
     sentinels; every kernel path (TMA stream-K incl. fix-up, generic incl. split reduce, vector) must leave the
