@@ -178,7 +178,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from pspace_b200.device import DeviceContainer, fill_synthetic, fp64_peak
-    from pspace_b200.sharded import shard_bounds
+    from pspace_b200.sharded import ShardedProjector, shard_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -267,15 +267,13 @@ def run_b200(args):
         del J, Jflat
         torch.cuda.empty_cache()
 
+        sp = ShardedProjector(c, rank, world) if world > 1 else None
+
         def e2e_step():
             if world == 1:
                 c.projectMatrixHost(Jh, 0, wi, 0, wj, out=Ch)             # pspace_cuda_project_matrix_host
             else:
-                Jd = Jh.to(dev, non_blocking=True)
-                c.projectMatrix(Jd, 0, wi, 0, wj, q0=q0, q1=q1, out=C)
-                dist.all_reduce(Cr, op=dist.ReduceOp.SUM)
-                Ch.copy_(C, non_blocking=True)
-                torch.cuda.synchronize()
+                sp.projectMatrixHost(Jh, Ch, 0, wi, 0, wj, dev_out=C)     # hostin -> NCCL allreduce -> pinned host
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -288,8 +286,8 @@ def run_b200(args):
         e2e = {"value": updates * args.steps / float(dt.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(Jh.numel() * Jh.element_size()), "d2h_bytes_per_step": int(Ch.numel() * Ch.element_size()),
                "ms_per_step": float(dt.item()) / args.steps * 1e3,
-               "api": "pspace_cuda_project_matrix_host (C-ABI, pinned host J -> host C)" if world == 1 else
-                      "ShardedProjector host path: pinned host J shard -> device, project, NCCL allreduce, C -> pinned host; bytes are per rank"}
+               "api": "pspace_cuda_project_matrix_host (C-ABI, pinned host J -> host C; J uploaded in slabs overlapped with the projection)" if world == 1 else
+                      "ShardedProjector.projectMatrixHost: pspace_cuda_project_matrix_hostin (slab-pipelined upload of the pinned J shard) -> NCCL allreduce -> C to pinned host; bytes are per rank"}
 
     if rank != 0:
         if world > 1:

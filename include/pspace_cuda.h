@@ -133,6 +133,10 @@ int pspace_cuda_project_matrix(const pspace_ctx *ctx, const pspace_project_args 
  * arrays in, host array out; H2D + kernels + D2H inside, synchronous). */
 int pspace_cuda_project_vector_host(pspace_ctx *ctx, const pspace_project_args *a, const double *h_f, double *h_F);
 int pspace_cuda_project_matrix_host(pspace_ctx *ctx, const pspace_project_args *a, const double *h_J, double *h_C);
+/* Host input, DEVICE output (complete on return): for callers that combine the result on the device first
+ * (multi-GPU allreduce) before reading it back.  The host forms upload J in slabs of quadrature points through a
+ * double buffer, overlapping the upload of slab s+1 with the projection of slab s (option "slab_mb"). */
+int pspace_cuda_project_matrix_hostin(pspace_ctx *ctx, const pspace_project_args *a, const double *h_J, double *d_C);
 
 /* ---- (f1) polynomial-chaos expansion evaluated at quadrature points -------------------------------------
  * U[q][c] = sum_{k in [k0,k1)} psi_k(z_q) V[k-k0][c]  for q in [q0,q1);  d_V[(k1-k0)][ncols], d_U[(q1-q0)][ncols]
@@ -176,7 +180,8 @@ int pspace_cuda_memcpy(void *dst, const void *src, size_t bytes, int to_device);
 long long pspace_cuda_launch_count(const pspace_ctx *ctx);
 /* tuning / test switches.  "force_generic" = 1: use the all-warps cp.async projection kernel even where the
  * TMA warp-specialised kernel applies (the generic kernel is otherwise used only for operands TMA cannot
- * address: odd column counts or unaligned bases). */
+ * address: odd column counts or unaligned bases).  "panel_cache" = 0: rebuild the basis panels on every call.
+ * "slab_mb" = n: upload slab size of the host-input forms. */
 int pspace_cuda_set_option(pspace_ctx *ctx, const char *name, int value);
 /* description + FLOP count of the kernel the last project call used */
 int pspace_cuda_last_plan(const pspace_ctx *ctx, char *buf, int buflen);

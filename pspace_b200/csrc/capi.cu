@@ -63,6 +63,10 @@ int pspace_cuda_destroy(pspace_ctx *c) {
   cudaFree(c->d_panel);
   cudaFree(c->d_scratch_in); cudaFree(c->d_scratch_out); cudaFree(c->d_scratch_ws);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->copy_stream) {
+    cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_copy[i]); cudaEventDestroy(c->ev_comp[i]); }
+  }
   delete c;
   return PSPACE_OK;
 }
@@ -240,25 +244,71 @@ static int ensure(void **buf, size_t *have, size_t need) {
   return PSPACE_OK;
 }
 
+// Host-input projection: the rows of f / J stream from host memory in slabs of quadrature points through a
+// double buffer — slab s+1 is uploaded on the copy stream while slab s is projected (accumulating into d_out) on the
+// compute stream — so only the first slab's upload is exposed and the device never holds more than two slabs of J.
+// Pinned host memory makes the uploads truly asynchronous; pageable memory works too (staged by the driver).
+static int project_hostin(pspace_ctx *c, int is_matrix, const pspace_project_args *a, const double *h_in, double *d_out) {
+  PS_CUDA(cudaSetDevice(c->device));
+  if (!c->own_stream) PS_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  if (!c->copy_stream) {
+    PS_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      PS_CUDA(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+      PS_CUDA(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t st = c->own_stream, cs = c->copy_stream;
+  const size_t w = c->width;
+  const long long nq = a->q1 - a->q0;
+  const size_t row_bytes = sizeof(double) * w * a->ncols;
+  const size_t in_bytes = row_bytes * (size_t)nq;
+  const size_t target = c->slab_bytes > 0 ? (size_t)c->slab_bytes : ((size_t)384 << 20);
+  long long nslab = (long long)((in_bytes + target - 1) / target);
+  nslab = nslab < 1 ? 1 : (nslab > 64 ? 64 : nslab);
+  long long slab_rows = (nq + nslab - 1) / nslab;
+  slab_rows = (slab_rows + 31) / 32 * 32;                       // keep every K-chunk of a slab full
+  if (slab_rows < 32) slab_rows = 32;
+  nslab = nq > 0 ? (nq + slab_rows - 1) / slab_rows : 0;
+  int rc;
+  if ((rc = ensure(&c->d_scratch_in, &c->scratch_in_bytes, (nslab > 1 ? 2 : 1) * row_bytes * (size_t)slab_rows))) return rc;
+  pspace_project_args as = *a;
+  as.q0 = a->q0; as.q1 = a->q0 + (nq < slab_rows ? nq : slab_rows);
+  const size_t ws = ps_project_workspace(c, is_matrix, &as);      // the first slab is the largest
+  if ((rc = ensure(&c->d_scratch_ws, &c->scratch_ws_bytes, ws))) return rc;
+  if (nslab == 0) return ps_project(c, is_matrix, a, nullptr, d_out, c->d_scratch_ws, ws, st);
+  for (long long s = 0; s < nslab; s++) {
+    const int b = (int)(s & 1);
+    const long long r0 = s * slab_rows, r1 = (r0 + slab_rows < nq) ? r0 + slab_rows : nq;
+    double *buf = (double *)((unsigned char *)c->d_scratch_in + (size_t)b * row_bytes * (size_t)slab_rows);
+    if (s >= 2) PS_CUDA(cudaStreamWaitEvent(cs, c->ev_comp[b], 0));        // buffer b is free again
+    PS_CUDA(cudaMemcpyAsync(buf, (const unsigned char *)h_in + (size_t)r0 * row_bytes, (size_t)(r1 - r0) * row_bytes,
+                            cudaMemcpyHostToDevice, cs));
+    PS_CUDA(cudaEventRecord(c->ev_copy[b], cs));
+    PS_CUDA(cudaStreamWaitEvent(st, c->ev_copy[b], 0));
+    as = *a;
+    as.q0 = a->q0 + r0; as.q1 = a->q0 + r1;
+    as.accumulate = (s > 0) ? 1 : a->accumulate;
+    rc = ps_project(c, is_matrix, &as, buf, d_out, c->d_scratch_ws, ws, st);
+    if (rc) return rc;
+    PS_CUDA(cudaEventRecord(c->ev_comp[b], st));
+  }
+  return PSPACE_OK;
+}
+
 static int project_host(pspace_ctx *c, int is_matrix, const pspace_project_args *a, const double *h_in, double *h_out) {
   if (!c || !a || !h_in || !h_out) return ps_fail(PSPACE_EINVAL, "null argument");
   PS_CUDA(cudaSetDevice(c->device));
-  if (!c->own_stream) PS_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-  cudaStream_t st = c->own_stream;
-  const size_t w = c->width;
   if (a->q1 < a->q0 || a->k1 < a->k0 || (is_matrix && a->j1 < a->j0)) return ps_fail(PSPACE_EINVAL, "range");
-  const size_t in_bytes = sizeof(double) * w * (size_t)(a->q1 - a->q0) * a->ncols;
+  const size_t w = c->width;
   const size_t rows = is_matrix ? (size_t)(a->k1 - a->k0) * (a->j1 - a->j0) : (size_t)(a->k1 - a->k0);
   const size_t out_bytes = sizeof(double) * w * rows * a->ncols;
-  const size_t ws = ps_project_workspace(c, is_matrix, a);
   int rc;
-  if ((rc = ensure(&c->d_scratch_in, &c->scratch_in_bytes, in_bytes))) return rc;
   if ((rc = ensure(&c->d_scratch_out, &c->scratch_out_bytes, out_bytes))) return rc;
-  if ((rc = ensure(&c->d_scratch_ws, &c->scratch_ws_bytes, ws))) return rc;
-  PS_CUDA(cudaMemcpyAsync(c->d_scratch_in, h_in, in_bytes, cudaMemcpyHostToDevice, st));
+  if (!c->own_stream) PS_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  cudaStream_t st = c->own_stream;
   if (a->accumulate) PS_CUDA(cudaMemcpyAsync(c->d_scratch_out, h_out, out_bytes, cudaMemcpyHostToDevice, st));
-  rc = ps_project(c, is_matrix, a, (const double *)c->d_scratch_in, (double *)c->d_scratch_out, c->d_scratch_ws, ws, st);
-  if (rc) return rc;
+  if ((rc = project_hostin(c, is_matrix, a, h_in, (double *)c->d_scratch_out))) return rc;
   PS_CUDA(cudaMemcpyAsync(h_out, c->d_scratch_out, out_bytes, cudaMemcpyDeviceToHost, st));
   PS_CUDA(cudaStreamSynchronize(st));
   return PSPACE_OK;
@@ -269,6 +319,14 @@ int pspace_cuda_project_vector_host(pspace_ctx *c, const pspace_project_args *a,
 }
 int pspace_cuda_project_matrix_host(pspace_ctx *c, const pspace_project_args *a, const double *h_J, double *h_C) {
   return project_host(c, 1, a, h_J, h_C);
+}
+int pspace_cuda_project_matrix_hostin(pspace_ctx *c, const pspace_project_args *a, const double *h_J, double *d_C) {
+  if (!c || !a || !h_J || !d_C) return ps_fail(PSPACE_EINVAL, "null argument");
+  if (a->q1 < a->q0 || a->k1 < a->k0 || a->j1 < a->j0) return ps_fail(PSPACE_EINVAL, "range");
+  int rc = project_hostin(c, 1, a, h_J, d_C);
+  if (rc) return rc;
+  PS_CUDA(cudaStreamSynchronize(c->own_stream));
+  return PSPACE_OK;
 }
 
 /* CUDA-runtime shims for host code that is compiled without CUDA headers (libpspace.so) */
@@ -294,6 +352,7 @@ long long pspace_cuda_launch_count(const pspace_ctx *c) { return c ? c->launches
 int pspace_cuda_set_option(pspace_ctx *c, const char *name, int value) {
   if (!c || !name) return ps_fail(PSPACE_EINVAL, "null argument");
   if (!strcmp(name, "force_generic")) { c->force_generic = value; return PSPACE_OK; }
+  if (!strcmp(name, "slab_mb")) { c->slab_bytes = (long long)value << 20; return PSPACE_OK; }
   if (!strcmp(name, "panel_cache")) { c->panel_cache = value; c->panel_valid = false; return PSPACE_OK; }
   return ps_fail(PSPACE_EINVAL, "unknown option %s", name);
 }

@@ -37,7 +37,9 @@ struct pspace_ctx {
   // scratch owned by the context for the host-buffer entry points
   void *d_scratch_in = nullptr, *d_scratch_out = nullptr, *d_scratch_ws = nullptr;
   size_t scratch_in_bytes = 0, scratch_out_bytes = 0, scratch_ws_bytes = 0;
-  cudaStream_t own_stream = nullptr;
+  cudaStream_t own_stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr};
+  long long slab_bytes = 0;              // host-input path: bytes of J per upload slab (0 = 384 MiB)
 };
 
 // error plumbing (capi.cu)

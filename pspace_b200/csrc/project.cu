@@ -464,7 +464,9 @@ __global__ void __launch_bounds__(256) k_psi_panel(const __grid_constant__ Panel
   }
 }
 
-template <class TL>
+// MASKED = a basis-pair filter is present (tile list + masked epilogue); a separate instantiation so that the dense
+// kernel's code generation is not perturbed by the filter logic (it cost 1.3 % when it was a run-time branch).
+template <class TL, bool MASKED>
 __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__ ProjParams p,
                                                          const __grid_constant__ CUtensorMap tmapB,
                                                          const __grid_constant__ CUtensorMap tmapI,
@@ -491,7 +493,7 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
   // the pieces of each remainder tile in CTA order (deterministic).  No wave-quantisation tail.
   const int G = gridDim.x, gcta = blockIdx.x;
   const int nchunk = (int)((p.q1 - p.q0 + KQ - 1) / KQ);
-  const int ntiles = p.tile_list ? *p.tile_count : p.tiles_i * p.tiles_j * p.tiles_n;
+  const int ntiles = MASKED ? *p.tile_count : p.tiles_i * p.tiles_j * p.tiles_n;
   const int nfull = ntiles / G;
   const long long rem_units = (long long)(ntiles - nfull * G) * nchunk;
   const long long r0 = rem_units * gcta / G, r1 = rem_units * (gcta + 1) / G;
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
     } else {
       tile = nfull * G + (int)ta + 1; c0 = 0; c1 = (int)(r1 - (ta + 1) * nchunk); slot = 1;
     }
-    if (p.tile_list) tile = p.tile_list[tile];      // position in the compacted list -> tile id
+    if (MASKED) tile = p.tile_list[tile];           // position in the compacted list -> tile id
   };
 
   constexpr int NCW = (NT_WS - NPROD) / 32;     // consumer warps 0..7, producer warpgroup = warps 8..11
@@ -629,19 +631,19 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
         const int i = ibase + wgm * WM + a, j = jbase + g;
         rok = i < iend && j < jend;
         rowoff = (long long)(i - p.i0) * p.stride_i + (long long)(j - p.j0) * p.stride_j;
-        if (rok && p.mask) keep = p.mask[(size_t)i * p.mask_ld + j] != 0;
+        if (MASKED && rok) keep = p.mask[(size_t)i * p.mask_ld + j] != 0;
       } else {
         const int k = jbase + (wgm * WM + a) * 8 + g;
         rok = k < jend;
         rowoff = (long long)(k - p.j0) * p.stride_j;
       }
       if (!rok) continue;
-      if (!keep && p.accumulate) continue;          // filtered pair: contributes nothing
+      if (MASKED && !keep && p.accumulate) continue;          // filtered pair: contributes nothing
 #pragma unroll
       for (int b = 0; b < WN; b++) {
         const int col = col0 + wgn * WN * 8 + b * 8 + 2 * kl;
         double *dst = p.out + rowoff + col;
-        double v0 = keep ? acc[a][b][0] : 0.0, v1 = keep ? acc[a][b][1] : 0.0;
+        double v0 = (!MASKED || keep) ? acc[a][b][0] : 0.0, v1 = (!MASKED || keep) ? acc[a][b][1] : 0.0;
         if (col + 1 < p.ncols_d && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
           if (p.accumulate) { const double2 o = *reinterpret_cast<double2 *>(dst); v0 += o.x; v1 += o.y; }
           *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
@@ -881,7 +883,8 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
     } else tmI = tmJ;
     static bool attr_ws = false;
     if (!attr_ws) {
-      PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      if (MAT) PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, MAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_ws = true;
     }
     p.out = d_out;
@@ -901,7 +904,8 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
       if (!a->accumulate) PS_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * pl.out_elems, st));
       fix_blocks = pl.sk_grid - 1;     // remainder tile count is only known on the device
     }
-    k_project_ws<TL><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
+    if (MAT && p.mask) k_project_ws<TL, MAT><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);   // MAT == true here: the masked instantiation
+    else k_project_ws<TL, false><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
     PS_LAUNCH_CHECK(c);
     if (fix_blocks > 0) {
       k_fixup<<<fix_blocks, 256, 0, st>>>(p, pl.sk_grid, TL::BM, TL::BN, TL::BI, TL::NJ, MAT ? 1 : 0);

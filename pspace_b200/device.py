@@ -197,7 +197,7 @@ class DeviceContainer:
         return out
 
     def projectMatrixHost(self, J, i0=0, i1=None, j0=0, j1=None, q0=0, q1=None, out=None, accumulate=False):
-        """Host-buffer form (numpy or pinned torch CPU tensors in/out); copies are inside the call."""
+        """Host-buffer form (numpy or pinned torch CPU tensors in/out); copies are inside the call (J rows q0..q1-1)."""
         i1 = self.N if i1 is None else i1
         j1 = self.N if j1 is None else j1
         q1 = self.Q if q1 is None else q1
@@ -208,6 +208,19 @@ class DeviceContainer:
         on = out.numpy() if isinstance(out, torch.Tensor) else out
         a = self._args(i0, i1, j0, j1, q0, q1, m2, accumulate, 0, 0)
         check(self.L.pspace_cuda_project_matrix_host(self.h, ctypes.byref(a), Jn.ctypes.data, on.ctypes.data))
+        return out
+
+    def projectMatrixHostIn(self, J, out, i0=0, i1=None, j0=0, j1=None, q0=0, q1=None, accumulate=False):
+        """Host J rows (numpy / pinned torch CPU tensor) -> DEVICE tensor `out`, slab-pipelined upload; complete on return."""
+        i1 = self.N if i1 is None else i1
+        j1 = self.N if j1 is None else j1
+        q1 = self.Q if q1 is None else q1
+        Jn = J.numpy() if isinstance(J, torch.Tensor) else np.ascontiguousarray(J, dtype=self.np_dtype)
+        assert out.is_cuda and out.is_contiguous() and Jn.shape[0] == q1 - q0
+        a = self._args(i0, i1, j0, j1, q0, q1, Jn.shape[1], accumulate, 0, 0)
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().synchronize()
+            check(self.L.pspace_cuda_project_matrix_hostin(self.h, ctypes.byref(a), Jn.ctypes.data, out.data_ptr()))
         return out
 
     def projectVectorHost(self, f, k0=0, k1=None, q0=0, q1=None, out=None, accumulate=False):

@@ -91,6 +91,20 @@ class ShardedProjector:
         C = self.c.projectMatrix(J_local, i0, i1, j0, j1, q0=self.q0, q1=self.q1, out=out)
         return combine(C, mode, self.group)
 
+    def projectMatrixHost(self, J_local_host, out_host, i0=0, i1=None, j0=0, j1=None, dev_out=None):
+        """End-to-end host form: this rank's J rows in (pinned) host memory -> slab-pipelined upload + projection ->
+        allreduce on the device -> the combined block in `out_host` (pinned).  Returns out_host."""
+        i1 = self.c.N if i1 is None else i1
+        j1 = self.c.N if j1 is None else j1
+        m2 = J_local_host.shape[1]
+        if dev_out is None:
+            dev_out = torch.empty((i1 - i0, j1 - j0, m2), dtype=self.c.t_dtype, device=self.c.device)
+        self.c.projectMatrixHostIn(J_local_host, dev_out, i0, i1, j0, j1, q0=self.q0, q1=self.q1)
+        combine(dev_out, "allreduce", self.group)
+        out_host.copy_(dev_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host
+
     def projectVector(self, f_local, k0=0, k1=None, out=None, mode="allreduce"):
         F = self.c.projectVector(f_local, k0, k1, q0=self.q0, q1=self.q1, out=out)
         return combine(F, mode, self.group)

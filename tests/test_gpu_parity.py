@@ -384,6 +384,37 @@ def test_masked_projection_sparsity_filter(cplx):
     c.close()
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+def test_host_input_slab_pipeline(cplx):
+    """Host-buffer entry points upload J in slabs overlapped with the projection: many small slabs (forced with
+    slab_mb) must give the one-shot device result, incl. accumulate, ragged last slab and pageable memory."""
+    rng = np.random.default_rng(81)
+    ps = [("normal", 0.2 + (1e-30j if cplx else 0), 0.8, 4), ("uniform", -1.0, 1.5, 6), ("exponential", 0.5, 0.7, 5),
+          ("normal", 0.0, 1.0, 3)]
+    o = H.CpuContainer(H.oracle_api(cplx), ps, 1).initialize()          # Q = 5*7*6*4 = 840
+    c = _dc(ps, 1, cplx).initialize()
+    m2 = 576
+    J = rng.normal(size=(o.Q, m2)).astype(o.dtype)
+    if cplx:
+        J = J + 1j * rng.normal(size=J.shape)
+    ref = c.projectMatrix(torch.from_numpy(J).cuda(), 0, 20, 0, 30).cpu().numpy()
+    assert normwise(ref, o.project_matrix(J, 0, 20, 0, 30, nthreads=8)) < TOL
+    c.setOption("slab_mb", 1)                                          # 1 MiB slabs -> 4-8 slabs of 224/96 points
+    got = c.projectMatrixHost(J, 0, 20, 0, 30)
+    assert normwise(got, ref) < 1e-13
+    Jp = torch.from_numpy(J).pin_memory()
+    out = torch.full((20, 30, m2), 2.0, dtype=Jp.dtype).pin_memory()
+    c.projectMatrixHost(Jp, 0, 20, 0, 30, out=out, accumulate=True)
+    assert normwise(out.numpy(), ref + 2.0) < 1e-13
+    dev = torch.empty((20, 30, m2), dtype=Jp.dtype, device="cuda")
+    c.projectMatrixHostIn(Jp[100:700], dev, 0, 20, 0, 30, q0=100, q1=700)
+    part = c.projectMatrix(torch.from_numpy(J[100:700]).cuda(), 0, 20, 0, 30, q0=100, q1=700)
+    assert normwise(dev.cpu().numpy(), part.cpu().numpy()) < 1e-13
+    f = J[:, :24].copy()
+    assert normwise(c.projectVectorHost(f), c.projectVector(torch.from_numpy(f).cuda()).cpu().numpy()) < 1e-13
+    c.close()
+
+
 def test_no_write_outside_the_output_window():
     """compute-sanitizer is closed on this pool: own bounds check.  The output sits inside a larger buffer of
     sentinels; every kernel path (TMA stream-K incl. fix-up, generic incl. split reduce, vector) must leave the
