@@ -122,6 +122,11 @@ typedef struct {
    * TACSStochasticElement.cpp:7-21).  Pairs with mask 0 are structurally zero: their blocks are written as 0
    * (left untouched when accumulate = 1) and tiles without any kept pair are skipped.  NULL = all pairs. */
   const unsigned char *d_pair_mask;
+  /* matrix only, optional: 1 = exploit C[i][j] == C[j][i] (psi_i psi_j = psi_j psi_i): only tiles holding a pair
+   * j >= i are computed and each block is stored to (i,j) and (j,i).  Needs a square window (k0==j0, k1==j1).  The
+   * result is the same full window; about half the arithmetic.  The reference computes all N^2 ordered pairs
+   * (TACSStochasticElement.cpp:380-388), so this is off by default and reported separately by bench.py. */
+  int symmetric;
 } pspace_project_args;
 
 size_t pspace_cuda_project_workspace(const pspace_ctx *ctx, int is_matrix, const pspace_project_args *a);

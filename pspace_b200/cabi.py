@@ -21,7 +21,7 @@ class PspaceCudaError(RuntimeError):
 
 class ProjectArgs(ctypes.Structure):
     _fields_ = [("k0", _i), ("k1", _i), ("j0", _i), ("j1", _i), ("q0", _ll), ("q1", _ll),
-                ("ncols", _i), ("accumulate", _i), ("ksplit", _i), ("variant", _i), ("d_pair_mask", _vp)]
+                ("ncols", _i), ("accumulate", _i), ("ksplit", _i), ("variant", _i), ("d_pair_mask", _vp), ("symmetric", _i)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/pspace_cuda.h

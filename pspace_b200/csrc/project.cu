@@ -60,6 +60,7 @@ struct ProjParams {
   int mask_ld;                 // = N
   const int *tile_list;        // fast path with a mask: ids of the tiles that contain at least one kept pair ...
   const int *tile_count;       // ... and how many there are (device scalars: no host round trip)
+  int symmetric;               // matrix mode, square window: compute pairs j >= i only and mirror the block to (j,i)
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gptr, int src_bytes) {
@@ -499,7 +500,7 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
   const long long r0 = rem_units * gcta / G, r1 = rem_units * (gcta + 1) / G;
   const int nseg = nfull + (r1 > r0 ? 1 : 0) + ((r1 > r0 && r1 > (r0 / nchunk + 1) * (long long)nchunk) ? 1 : 0);
   auto segment = [&](int sidx, int &tile, int &c0, int &c1, int &slot) {
-    if (sidx < nfull) { tile = sidx * G + gcta; c0 = 0; c1 = nchunk; slot = -1; return; }
+    if (sidx < nfull) { tile = sidx * G + gcta; if (MASKED) tile = p.tile_list[tile]; c0 = 0; c1 = nchunk; slot = -1; return; }
     const long long ta = r0 / nchunk;
     if (sidx == nfull) {
       tile = nfull * G + (int)ta; c0 = (int)(r0 - ta * nchunk); c1 = (int)min((long long)nchunk, r1 - ta * nchunk); slot = 0;
@@ -624,21 +625,23 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
     } else {
 #pragma unroll
     for (int a = 0; a < WM; a++) {
-      long long rowoff;
+      long long rowoff, mirroff = -1;
       bool rok;
       bool keep = true;
       if (MAT) {
         const int i = ibase + wgm * WM + a, j = jbase + g;
         rok = i < iend && j < jend;
         rowoff = (long long)(i - p.i0) * p.stride_i + (long long)(j - p.j0) * p.stride_j;
-        if (MASKED && rok) keep = p.mask[(size_t)i * p.mask_ld + j] != 0;
+        if (MASKED && rok) keep = p.symmetric ? (j >= i) : (p.mask[(size_t)i * p.mask_ld + j] != 0);
+        if (MASKED && p.symmetric && rok && j > i)      // mirrored block (j,i) of the same window
+          mirroff = (long long)(j - p.i0) * p.stride_i + (long long)(i - p.j0) * p.stride_j;
       } else {
         const int k = jbase + (wgm * WM + a) * 8 + g;
         rok = k < jend;
         rowoff = (long long)(k - p.j0) * p.stride_j;
       }
       if (!rok) continue;
-      if (MASKED && !keep && p.accumulate) continue;          // filtered pair: contributes nothing
+      if (MASKED && !keep && (p.accumulate || p.symmetric)) continue;   // filtered pair: nothing to add / written by its mirror
 #pragma unroll
       for (int b = 0; b < WN; b++) {
         const int col = col0 + wgn * WN * 8 + b * 8 + 2 * kl;
@@ -651,6 +654,12 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
           if (col < p.ncols_d) dst[0] = p.accumulate ? dst[0] + v0 : v0;
           if (col + 1 < p.ncols_d) dst[1] = p.accumulate ? dst[1] + v1 : v1;
         }
+        if (MASKED && mirroff >= 0) {
+          double *md = p.out + mirroff + col;
+          double w0 = acc[a][b][0], w1 = acc[a][b][1];
+          if (col < p.ncols_d) md[0] = p.accumulate ? md[0] + w0 : w0;
+          if (col + 1 < p.ncols_d) md[1] = p.accumulate ? md[1] + w1 : w1;
+        }
       }
     }
     }
@@ -660,8 +669,8 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
 
 // With a pair mask: ids of the tiles (tn fastest, tj, ti) that hold at least one kept pair, in increasing id order.
 // Single block: the tile count is small (cfg5: 3888) and the order must be reproducible.
-__global__ void __launch_bounds__(256) k_tile_list(const unsigned char *mask, int mask_ld, int i0, int ni, int j0, int nj,
-                                                   int tiles_i, int tiles_j, int tiles_n, int BI, int *list, int *count) {
+__global__ void __launch_bounds__(256) k_tile_list(const unsigned char *mask, int mask_ld, int symmetric, int i0, int ni, int j0,
+                                                   int nj, int tiles_i, int tiles_j, int tiles_n, int BI, int *list, int *count) {
   __shared__ int base;
   __shared__ int wsum[8];
   if (threadIdx.x == 0) base = 0;
@@ -677,7 +686,7 @@ __global__ void __launch_bounds__(256) k_tile_list(const unsigned char *mask, in
         if (i >= i0 + ni) break;
         for (int b = 0; b < 8; b++) {
           const int j = j0 + tj * 8 + b;
-          if (j < j0 + nj && mask[(size_t)i * mask_ld + j]) { any = 1; break; }
+          if (j < j0 + nj && (symmetric ? (j >= i) : (mask[(size_t)i * mask_ld + j] != 0))) { any = 1; break; }
         }
       }
     }
@@ -727,13 +736,16 @@ __global__ void __launch_bounds__(256) k_fixup(const __grid_constant__ ProjParam
     }
     const int col = col0 + cc;
     if (col >= p.ncols_d) continue;
-    long long rowoff;
+    long long rowoff, mirroff = -1;
     bool rok;
     if (matrix) {
       const int i = ibase + r / 8, j = jbase + (r & 7);
       rok = i < iend && j < jend;
       rowoff = (long long)(i - p.i0) * p.stride_i + (long long)(j - p.j0) * p.stride_j;
-      if (rok && p.mask && p.mask[(size_t)i * p.mask_ld + j] == 0) { if (p.accumulate) continue; sum = 0.0; }
+      if (rok && p.symmetric) {
+        if (j < i) continue;
+        if (j > i) mirroff = (long long)(j - p.i0) * p.stride_i + (long long)(i - p.j0) * p.stride_j;
+      } else if (rok && p.mask && p.mask[(size_t)i * p.mask_ld + j] == 0) { if (p.accumulate) continue; sum = 0.0; }
     } else {
       const int k = jbase + r;
       rok = k < jend;
@@ -742,6 +754,7 @@ __global__ void __launch_bounds__(256) k_fixup(const __grid_constant__ ProjParam
     if (!rok) continue;
     double *dst = p.out + rowoff + col;
     *dst = p.accumulate ? *dst + sum : sum;
+    if (mirroff >= 0) { double *md = p.out + mirroff + col; *md = p.accumulate ? *md + sum : sum; }
   }
 }
 
@@ -892,19 +905,19 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
     p.sk_ws = (double *)d_ws;
     int fix_blocks = pl.sk_rem_tiles;
     int *d_list = nullptr;
-    if (p.mask) {
-      // tile list on the device; untouched tiles must read as zero
+    if (p.mask || p.symmetric) {
+      // tile list on the device; with a mask untouched tiles must read as zero (symmetric mode writes every block)
       const int ntl = p.tiles_i * p.tiles_j * p.tiles_n;
       PS_CUDA(cudaMallocAsync(&d_list, sizeof(int) * (ntl + 1), st));
-      k_tile_list<<<1, 256, 0, st>>>(p.mask, p.mask_ld, p.i0, p.ni, p.j0, p.nj, p.tiles_i, p.tiles_j, p.tiles_n, TL::BI,
+      k_tile_list<<<1, 256, 0, st>>>(p.mask, p.mask_ld, p.symmetric, p.i0, p.ni, p.j0, p.nj, p.tiles_i, p.tiles_j, p.tiles_n, TL::BI,
                                      d_list + 1, d_list);
       PS_LAUNCH_CHECK(c);
       p.tile_list = d_list + 1;
       p.tile_count = d_list;
-      if (!a->accumulate) PS_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * pl.out_elems, st));
+      if (!a->accumulate && !p.symmetric) PS_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * pl.out_elems, st));
       fix_blocks = pl.sk_grid - 1;     // remainder tile count is only known on the device
     }
-    if (MAT && p.mask) k_project_ws<TL, MAT><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);   // MAT == true here: the masked instantiation
+    if (MAT && (p.mask || p.symmetric)) k_project_ws<TL, MAT><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);   // MAT == true here: the masked instantiation
     else k_project_ws<TL, false><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
     PS_LAUNCH_CHECK(c);
     if (fix_blocks > 0) {
@@ -1033,7 +1046,7 @@ int make_plan(const pspace_ctx *c, int is_matrix, const pspace_project_args *a, 
   // fast path (possible when the real column count is even; the operand's alignment is only known at launch)
   pl.sk_grid = (int)std::max<long long>(1, std::min<long long>(sm_count(c->device), ntiles * pl.nchunk));
   pl.sk_rem_tiles = (int)(ntiles % pl.sk_grid);
-  pl.ws_streamk = (ncols_d % 2 == 0 && (pl.sk_rem_tiles > 0 || (is_matrix && a->d_pair_mask))) ? (size_t)pl.sk_grid * 2 * v.BM * v.BN * sizeof(double) : 0;
+  pl.ws_streamk = (ncols_d % 2 == 0 && (pl.sk_rem_tiles > 0 || (is_matrix && (a->d_pair_mask || a->symmetric)))) ? (size_t)pl.sk_grid * 2 * v.BM * v.BN * sizeof(double) : 0;
   pl.ws_bytes = std::max(pl.ws_generic, pl.ws_streamk);
   return PSPACE_OK;
 }
@@ -1106,6 +1119,13 @@ int ps_project(const pspace_ctx *c, int is_matrix, const pspace_project_args *a,
   }
   p.out = d_out; p.slice_stride = 0; p.accumulate = a->accumulate; p.sk_ws = nullptr;
   p.mask = is_matrix ? a->d_pair_mask : nullptr; p.mask_ld = c->N; p.tile_list = nullptr; p.tile_count = nullptr;
+  p.symmetric = 0;
+  if (is_matrix && a->symmetric) {
+    if (a->k0 != a->j0 || a->k1 != a->j1) return ps_fail(PSPACE_EINVAL, "symmetric projection needs a square window (i range == j range)");
+    if (a->d_pair_mask) return ps_fail(PSPACE_EINVAL, "symmetric and d_pair_mask cannot be combined");
+    // only the TMA kernel implements it; operands it cannot address take the dense generic kernel (same result)
+    p.symmetric = (p.vec16 && !c->force_generic) ? 1 : 0;
+  }
 
   const Variant &v = (is_matrix ? MAT_VARIANTS : VEC_VARIANTS)[pl.variant_idx];
   const int key = (is_matrix ? 0 : 100) + (c->is_complex ? 10 : 0) + v.id;
@@ -1132,7 +1152,7 @@ int ps_project(const pspace_ctx *c, int is_matrix, const pspace_project_args *a,
   // plan record (bench / DESIGN): executed FLOP = 2 * rows * cols * q per real FMA, x2 again for the two
   // DMMA passes of the complex build (= 8 FLOP per complex FMA)
   const double rows = is_matrix ? (double)p.ni * p.nj : (double)p.nj;
-  mc->plan_flop = 2.0 * rows * (double)ncols_d * (double)(a->q1 - a->q0) * (c->is_complex ? 2.0 : 1.0);
+  mc->plan_flop = 2.0 * rows * (double)ncols_d * (double)(a->q1 - a->q0) * (c->is_complex ? 2.0 : 1.0);   // useful (all ordered pairs)
   char buf[256];
   snprintf(buf, sizeof buf, "%s%s [%s] tiles=%dx%dx%d chunks=%lld ctas=%d streamk_tiles=%d ksplit(generic)=%d", c->is_complex ? "z " : "",
            v.name, c->plan_kernel, pl.tiles_i, pl.tiles_j, pl.tiles_n, pl.nchunk, pl.sk_grid, pl.sk_rem_tiles, pl.ksplit);

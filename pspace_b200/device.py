@@ -150,9 +150,9 @@ class DeviceContainer:
         return out
 
     # ---- projections ---------------------------------------------------------------------------------
-    def _args(self, k0, k1, j0, j1, q0, q1, ncols, accumulate, ksplit, variant, mask=None):
+    def _args(self, k0, k1, j0, j1, q0, q1, ncols, accumulate, ksplit, variant, mask=None, symmetric=False):
         return ProjectArgs(k0, k1, j0, j1, q0, q1, ncols, int(accumulate), ksplit, variant,
-                           mask.data_ptr() if mask is not None else None)
+                           mask.data_ptr() if mask is not None else None, int(symmetric))
 
     def _workspace(self, is_matrix, a):
         need = self.L.pspace_cuda_project_workspace(self.h, is_matrix, ctypes.byref(a))
@@ -178,7 +178,7 @@ class DeviceContainer:
         return out
 
     def projectMatrix(self, J, i0=0, i1=None, j0=0, j1=None, q0=0, q1=None, out=None, accumulate=False, ksplit=0,
-                      variant=0, mask=None):
+                      variant=0, mask=None, symmetric=False):
         """C[i][j][c] = sum_q w_q psi_i psi_j J[q][c]; J holds rows q0..q1-1 (device tensor [q1-q0][m2])."""
         i1 = self.N if i1 is None else i1
         j1 = self.N if j1 is None else j1
@@ -189,7 +189,7 @@ class DeviceContainer:
             out = torch.empty((i1 - i0, j1 - j0, m2), dtype=self.t_dtype, device=self.device)
         if mask is not None:
             assert mask.is_cuda and mask.dtype == torch.uint8 and mask.shape == (self.N, self.N) and mask.is_contiguous()
-        a = self._args(i0, i1, j0, j1, q0, q1, m2, accumulate, ksplit, variant, mask)
+        a = self._args(i0, i1, j0, j1, q0, q1, m2, accumulate, ksplit, variant, mask, symmetric)
         ws, need = self._workspace(1, a)
         with torch.cuda.device(self.device):
             check(self.L.pspace_cuda_project_matrix(self.h, ctypes.byref(a), J.data_ptr(), out.data_ptr(),

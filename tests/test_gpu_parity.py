@@ -355,12 +355,12 @@ def test_masked_projection_sparsity_filter(cplx):
     for dmapf in ([1, 1, 1], [0, 2, 1], [3, 3, 3], [0, 0, 0]):
         maskh = H.pair_mask(o.degrees(), dmapf)
         mask = c.pairMask(dmapf)
-        for m2 in (4, 64, 9):
+        for m2 in (4, 64, 9, 576):        # 576: more kept tiles than SMs -> full data-parallel wave + stream-K remainder
             J = rng.normal(size=(Q, m2)).astype(o.dtype)
             if cplx:
                 J = J + 1j * rng.normal(size=J.shape)
             Jd = torch.from_numpy(J).cuda()
-            dense = o.project_matrix(J, nthreads=4)
+            dense = o.project_matrix(J, nthreads=8)
             ref = dense * maskh[:, :, None]
             for force in (0, 1):
                 c.setOption("force_generic", force)
@@ -412,6 +412,34 @@ def test_host_input_slab_pipeline(cplx):
     assert normwise(dev.cpu().numpy(), part.cpu().numpy()) < 1e-13
     f = J[:, :24].copy()
     assert normwise(c.projectVectorHost(f), c.projectVector(torch.from_numpy(f).cuda()).cpu().numpy()) < 1e-13
+    c.close()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_symmetric_projection_matches_dense(cplx):
+    """symmetric=1 computes pairs j >= i only and mirrors: same full window as the dense projection (the mirrored
+    half is bitwise equal to its source block), for full and sub-square windows, with accumulate."""
+    rng = np.random.default_rng(91)
+    ps = [("normal", 0.2 + (1e-30j if cplx else 0), 0.8, 3), ("uniform", -1.0, 1.5, 4), ("exponential", 0.5, 0.7, 3)]
+    o = H.CpuContainer(H.oracle_api(cplx), ps, 0).initialize()            # N = Q = 80
+    c = _dc(ps, 0, cplx).initialize()
+    N, Q = o.N, o.Q
+    for m2 in (4, 64, 576):
+        J = rng.normal(size=(Q, m2)).astype(o.dtype)
+        if cplx:
+            J = J + 1j * rng.normal(size=J.shape)
+        Jd = torch.from_numpy(J).cuda()
+        for (a0, a1) in ((0, N), (7, 53), (N - 3, N)):
+            ref = o.project_matrix(J, a0, a1, a0, a1, nthreads=8)
+            got = c.projectMatrix(Jd, a0, a1, a0, a1, symmetric=True).cpu().numpy()
+            assert normwise(got, ref) < TOL, (m2, a0)
+            assert np.array_equal(got, np.swapaxes(got, 0, 1))               # exact mirror
+            base = torch.full((a1 - a0, a1 - a0, m2), -1.5, dtype=Jd.dtype, device="cuda")
+            acc = c.projectMatrix(Jd, a0, a1, a0, a1, out=base, accumulate=True, symmetric=True).cpu().numpy()
+            assert normwise(acc, ref - 1.5) < TOL
+    from pspace_b200.cabi import PspaceCudaError
+    with pytest.raises(PspaceCudaError):
+        c.projectMatrix(Jd, 0, 10, 1, 11, symmetric=True)                     # not a square window
     c.close()
 
 
