@@ -1,0 +1,112 @@
+"""GPU parity at BASELINE.json's FULL sizes (cfg5: 10 parameters, N = 286, Q = 4^10 = 1 048 576, 24x24 blocks;
+cfg4: 8 Gaussian parameters, N = Q = 65 536, complex).  The oracle cannot run the whole projection in seconds, so
+these use (a) the oracle on a small pair window over ALL quadrature points and (b) size-independent properties:
+orthonormality (constant J -> identity blocks; the reference's own invariant, tests/test.py:131), linearity,
+additivity over quadrature-point shards, symmetry in (i,j), weights summing to one (pspace/core.py:181,229,276)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import harness as H  # noqa: E402
+from pspace_b200 import workloads as WL  # noqa: E402
+from tests.util import normwise  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def cfg5():
+    from pspace_b200.device import DeviceContainer, fill_synthetic
+    w = WL.cfg5()
+    c = DeviceContainer(w.params, w.basis_type, False).initialize()
+    assert (c.N, c.Q) == (286, 1048576)
+    J = fill_synthetic(c.Q * w.m2, w.seed + 1000).reshape(c.Q, w.m2)
+    yield w, c, J
+    c.close()
+
+
+def test_cfg5_integer_and_grid_kernels_vs_extended_oracle(cfg5):
+    w, c, _ = cfg5
+    o = H.CpuContainer(H.oracle_api(False), w.params, w.basis_type).initialize()
+    assert np.array_equal(c.degrees(), o.degrees())                       # 286 x 10 ints out of 4^10 tuples: bit-exact
+    W = c.weights()
+    assert abs(W.sum() - 1.0) < 1e-12
+    Zo, Yo, Wo = o.grid()
+    assert np.array_equal(W, Wo)                                          # 1M weights: bit-exact
+    Z, Y, _ = c.grid(500000, 500064)
+    assert np.array_equal(Z.cpu().numpy(), Zo[500000:500064]) and np.array_equal(Y.cpu().numpy(), Yo[500000:500064])
+    psi = c.evalBasisGrid(0, c.N, 777000, 777128).cpu().numpy()
+    assert np.array_equal(psi, o.basis_at(Zo[777000:777128]))             # basis values: bit-exact (degree <= 3)
+
+
+def test_cfg5_window_vs_oracle_over_all_points(cfg5):
+    w, c, J = cfg5
+    o = H.CpuContainer(H.oracle_api(False), w.params, w.basis_type).initialize()
+    Jh = J.cpu().numpy()
+    i0, i1, j0, j1 = 141, 143, 283, 286                                   # 2 x 3 pairs, away from the origin
+    ref = o.project_matrix(Jh, i0, i1, j0, j1, nthreads=2)
+    got = c.projectMatrix(J, i0, i1, j0, j1).cpu().numpy()
+    assert normwise(got, ref) < 1e-12
+    F = c.projectVector(J[:, :24].contiguous(), 100, 104).cpu().numpy()
+    assert normwise(F, o.project_vector(np.ascontiguousarray(Jh[:, :24]), 100, 104)) < 1e-12
+
+
+def test_cfg5_full_projection_properties(cfg5):
+    w, c, J = cfg5
+    N, Q, m2 = c.N, c.Q, w.m2
+    C = c.projectMatrix(J)                                                # the bench step: 8.58e10 updates
+    # symmetry in (i, j): psi_i psi_j = psi_j psi_i (the two halves come from different tiles / summation orders)
+    assert float((C - C.transpose(0, 1)).abs().max()) < 1e-12 * float(C.abs().max())
+    # the symmetric mode delivers the same window
+    Cs = c.projectMatrix(J, symmetric=True)
+    assert float((Cs - C).abs().max()) < 1e-12 * float(C.abs().max())
+    del Cs
+    # additivity over two quadrature-point shards (the multi-GPU decomposition), on a 64 x 286 window
+    qs = 524288 + 32 * 7
+    Ca = c.projectMatrix(J[:qs], 0, 64, 0, N, q0=0, q1=qs)
+    Cb = c.projectMatrix(J[qs:], 0, 64, 0, N, q0=qs, q1=Q)
+    assert float((Ca + Cb - C[:64]).abs().max()) < 1e-12 * float(C.abs().max())
+    del Ca, Cb
+    # orthonormality: J == 1 everywhere  ->  C[i][j][:] = delta_ij  (exact quadrature of degree <= 2p)
+    J1 = torch.ones((Q, 8), dtype=torch.float64, device="cuda")
+    I = c.projectMatrix(J1)
+    eye = torch.eye(N, dtype=torch.float64, device="cuda")[:, :, None].expand(N, N, 8)
+    assert float((I - eye).abs().max()) < 1e-11
+    # linearity in J on a window: P(2 J - 3 J1') = 2 P(J) - 3 P(J1')
+    Jw = J[:, :8].contiguous()
+    lhs = c.projectMatrix(2.0 * Jw - 3.0 * J1, 10, 40, 200, 286)
+    rhs = 2.0 * c.projectMatrix(Jw, 10, 40, 200, 286) - 3.0 * I[10:40, 200:286]
+    assert float((lhs - rhs).abs().max()) < 1e-12 * max(1.0, float(rhs.abs().max()))
+    # moments of a PC expansion: mean = coefficient 0, variance = sum of squares of the others
+    V = torch.randn((N, 4), dtype=torch.float64, device="cuda")
+    U = c.evaluateExpansion(V)
+    mean, _, var = c.moments(U)
+    assert float((mean - V[0]).abs().max()) < 1e-11
+    assert float((var - (V[1:] ** 2).sum(0)).abs().max()) < 1e-10
+    assert float((c.projectVector(U) - V).abs().max()) < 1e-11
+
+
+def test_cfg4_complex_window_vs_oracle():
+    """8 Gaussian parameters, tensor degree 3: N = Q = 65 536, 24x24 complex blocks, complex-step perturbed mean."""
+    from pspace_b200.device import DeviceContainer, fill_synthetic
+    w = WL.cfg4()
+    ps = [(k, a + (1e-30j if i == 0 else 0.0), b, d) for i, (k, a, b, d) in enumerate(w.params)]
+    c = DeviceContainer(ps, w.basis_type, True).initialize()
+    o = H.CpuContainer(H.oracle_api(True), ps, w.basis_type).initialize()
+    assert (c.N, c.Q) == (65536, 65536)
+    assert np.array_equal(c.degrees(), o.degrees())
+    J = fill_synthetic(c.Q * w.m2 * 2, w.seed + 1000).view(torch.complex128).reshape(c.Q, w.m2)
+    Jh = J.cpu().numpy()
+    i0, i1, j0, j1 = 40000, 40002, 65534, 65536
+    ref = o.project_matrix(Jh, i0, i1, j0, j1, nthreads=2)
+    got = c.projectMatrix(J, i0, i1, j0, j1).cpu().numpy()
+    assert normwise(got, ref) < 1e-12
+    # a 64 x 64 window like the benchmark's: symmetric under (i,j) exchange
+    Cw = c.projectMatrix(J, 0, 64, 0, 64)
+    assert float((Cw - Cw.transpose(0, 1)).abs().max()) < 1e-12 * float(Cw.abs().max())
+    # full vector projection (N = Q = 65536, m = 24) against the oracle on a few rows
+    f = J[:, :24].contiguous()
+    F = c.projectVector(f)
+    refF = o.project_vector(np.ascontiguousarray(Jh[:, :24]), 12345, 12348)
+    assert normwise(F[12345:12348].cpu().numpy(), refF) < 1e-12
+    c.close()
