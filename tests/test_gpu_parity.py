@@ -443,6 +443,50 @@ def test_symmetric_projection_matches_dense(cplx):
     c.close()
 
 
+@pytest.mark.parametrize("case", ["one_var_20pts", "eighteen_vars", "big_tables", "degree_zero_vars"])
+def test_edge_shapes_vs_oracle(case):
+    """Extremes of the supported range: a single parameter with the 20-point rules and degree 19; more than 16
+    parameters (32-byte digit rows); the largest 1-D tables the staged kernels accept; parameters of degree 0."""
+    rng = np.random.default_rng(101)
+    if case == "one_var_20pts":
+        ps, bt, m2 = [("normal", 0.5, 1.5, 19)], 0, 6
+    elif case == "eighteen_vars":
+        ps = [(("normal", "uniform", "exponential")[d % 3], 0.1 * d, 1.0 + 0.1 * d, 1) for d in range(18)]
+        ps[3] = (ps[3][0], ps[3][1], ps[3][2], 2)
+        bt, m2 = 1, 4                                            # complete degree 2: C(20,2) - (18-1)... N from the oracle
+        ps = [(k, a, b, d if i < 4 else (1 if i < 9 else 0)) for i, (k, a, b, d) in enumerate(ps)]   # Q = 2^8*3*... keep it small
+    elif case == "big_tables":
+        ps, bt, m2 = [("uniform", -1.0, 1.0, 9), ("exponential", 0.0, 1.0, 10), ("normal", 0.0, 1.0, 8)], 1, 8
+    else:
+        ps, bt, m2 = [("normal", 0.0, 1.0, 0), ("uniform", 0.0, 2.0, 3), ("exponential", 1.0, 1.0, 0), ("normal", 1.0, 2.0, 2)], 0, 5
+    o = H.CpuContainer(H.oracle_api(False), ps, bt).initialize()
+    c = _dc(ps, bt, False).initialize()
+    assert (c.N, c.Q) == (o.N, o.Q)
+    assert np.array_equal(c.degrees(), o.degrees())
+    Zo, Yo, Wo = o.grid()
+    Z, Y, W = (t.cpu().numpy() for t in c.grid())
+    deg5_legendre = any(k == "uniform" and d >= 5 for k, _, _, d in ps)
+    assert same_bits(W, Wo) and same_bits(Z, Zo) and same_bits(Y, Yo)
+    psi = c.evalBasisGrid().cpu().numpy()
+    ref_psi = o.basis_at(Zo)
+    if deg5_legendre:
+        assert normwise(psi, ref_psi) < 1e-12
+    else:
+        assert same_bits(psi, ref_psi)
+    J = rng.normal(size=(o.Q, m2))
+    Jd = torch.from_numpy(J).cuda()
+    i1, j1 = min(o.N, 24), min(o.N, 40)
+    ref = o.project_matrix(J, 0, i1, 0, j1, nthreads=8)
+    tol = 5e-11 if case == "one_var_20pts" else TOL      # degree-19 Hermite at |z| ~ 7: values ~1e6, reference-order cancellation
+    for force in (0, 1):
+        c.setOption("force_generic", force)
+        assert normwise(c.projectMatrix(Jd, 0, i1, 0, j1).cpu().numpy(), ref) < tol, (case, force)
+        assert normwise(c.projectVector(Jd).cpu().numpy(), o.project_vector(J)) < tol, (case, force)
+    V = rng.normal(size=(o.N, 3))
+    assert normwise(c.evaluateExpansion(torch.from_numpy(V).cuda()).cpu().numpy(), o.evaluate_expansion(V)) < tol
+    c.close()
+
+
 def test_no_write_outside_the_output_window():
     """compute-sanitizer is closed on this pool: own bounds check.  The output sits inside a larger buffer of
     sentinels; every kernel path (TMA stream-K incl. fix-up, generic incl. split reduce, vector) must leave the
