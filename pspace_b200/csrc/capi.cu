@@ -36,6 +36,15 @@ int pspace_cuda_create(pspace_ctx **out, int device, int is_complex, int nvars, 
   if (ndev == 0) return ps_fail(PSPACE_ECUDA, "no CUDA device: the pspace GPU path has no CPU fallback");
   if (device < 0 || device >= ndev) return ps_fail(PSPACE_EINVAL, "device %d outside 0..%d", device, ndev - 1);
   PS_CUDA(cudaSetDevice(device));
+  {
+    // scratch of the small kernels comes from the stream-ordered allocator: keep freed blocks in the pool instead of
+    // returning them to the driver at every synchronisation (a cudaMallocAsync would otherwise cost milliseconds)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   pspace_ctx *c = new pspace_ctx();
   c->device = device;
   c->is_complex = is_complex ? 1 : 0;

@@ -10,25 +10,49 @@
 #include <algorithm>
 
 namespace {
-constexpr int MT_X = 32, MT_Y = 8;     // 32 columns x 8 rows of quadrature points per block step
+constexpr int MT = 256;            // threads per block
+constexpr int MT_COLS = 128;       // widest column tile; wider f is covered by blockIdx.y
 
+// Thread t of a block owns column (t % ct) of the tile and the rows (t / ct) + k*R of the block's q-slice, so the
+// threads of a block read one contiguous run of R rows per step (fully coalesced), 4 steps in flight.
 template <bool CPLX>
-__global__ void __launch_bounds__(MT_X *MT_Y) k_moments_partial(const double *f, const double *W, long long q0, long long nq,
-                                                               int ncols, long long rows_per_slice, double *part /*[slices][2][ncols*width]*/) {
+__global__ void __launch_bounds__(MT) k_moments_partial(const double *f, const double *W, long long q0, long long nq,
+                                                         int ncols, int ct, long long rows_per_slice,
+                                                         double *part /*[slices][2][ncols*width]*/) {
   constexpr int WD = CPLX ? 2 : 1;
-  __shared__ double sm[MT_Y][MT_X][2 * WD];
-  const int tx = threadIdx.x % MT_X, ty = threadIdx.x / MT_X;
-  const int col = blockIdx.y * MT_X + tx;
+  __shared__ double sm[MT][2 * WD];
+  const int R = MT / ct;                               // rows handled in parallel
+  const int c_in = threadIdx.x % ct, rr = threadIdx.x / ct;
+  const int col = blockIdx.y * ct + c_in;
   const long long r0 = blockIdx.x * rows_per_slice, r1 = min(nq, r0 + rows_per_slice);
   double m_re = 0, m_im = 0, s_re = 0, s_im = 0;
-  if (col < ncols) {
-    for (long long r = r0 + ty; r < r1; r += MT_Y) {
-      if (!CPLX) {
-        const double w = W[q0 + r], v = f[r * ncols + col];
-        const double t = w * v;          // (w_q*psi_0)*f with psi_0 == 1
-        m_re += t;
-        s_re += t * v;
-      } else {
+  const bool active = rr < R && col < ncols;
+  if (active) {
+    long long r = r0 + rr;
+    for (; r + 3LL * R < r1; r += 4LL * R) {
+      double w[4][2], v[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const long long row = r + (long long)u * R;
+        if (!CPLX) { w[u][0] = W[q0 + row]; v[u][0] = f[row * ncols + col]; }
+        else {
+          w[u][0] = W[2 * (q0 + row)]; w[u][1] = W[2 * (q0 + row) + 1];
+          v[u][0] = f[2 * (row * ncols + col)]; v[u][1] = f[2 * (row * ncols + col) + 1];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (!CPLX) { const double t = w[u][0] * v[u][0]; m_re += t; s_re += t * v[u][0]; }
+        else {
+          const double tr = w[u][0] * v[u][0] - w[u][1] * v[u][1], ti = w[u][0] * v[u][1] + w[u][1] * v[u][0];
+          m_re += tr; m_im += ti;
+          s_re += tr * v[u][0] - ti * v[u][1]; s_im += tr * v[u][1] + ti * v[u][0];
+        }
+      }
+    }
+    for (; r < r1; r += R) {
+      if (!CPLX) { const double wv = W[q0 + r], v = f[r * ncols + col]; const double t = wv * v; m_re += t; s_re += t * v; }
+      else {
         const double wr = W[2 * (q0 + r)], wi = W[2 * (q0 + r) + 1];
         const double vr = f[2 * (r * ncols + col)], vi = f[2 * (r * ncols + col) + 1];
         const double tr = wr * vr - wi * vi, ti = wr * vi + wi * vr;
@@ -37,16 +61,16 @@ __global__ void __launch_bounds__(MT_X *MT_Y) k_moments_partial(const double *f,
       }
     }
   }
-  sm[ty][tx][0] = m_re; sm[ty][tx][WD] = s_re;
-  if (CPLX) { sm[ty][tx][1] = m_im; sm[ty][tx][WD + 1] = s_im; }
+  sm[threadIdx.x][0] = m_re; sm[threadIdx.x][WD] = s_re;
+  if (CPLX) { sm[threadIdx.x][1] = m_im; sm[threadIdx.x][WD + 1] = s_im; }
   __syncthreads();
-  if (ty == 0 && col < ncols) {
+  if (rr == 0 && col < ncols) {                        // fixed-order reduction over the R row groups
     double a[2 * WD];
 #pragma unroll
-    for (int k = 0; k < 2 * WD; k++) a[k] = sm[0][tx][k];
-    for (int y = 1; y < MT_Y; y++)
+    for (int k = 0; k < 2 * WD; k++) a[k] = sm[c_in][k];
+    for (int y = 1; y < R; y++)
 #pragma unroll
-      for (int k = 0; k < 2 * WD; k++) a[k] += sm[y][tx][k];
+      for (int k = 0; k < 2 * WD; k++) a[k] += sm[y * ct + c_in][k];
     double *dst = part + (size_t)blockIdx.x * 2 * ncols * WD;
 #pragma unroll
     for (int k = 0; k < WD; k++) { dst[col * WD + k] = a[k]; dst[(size_t)ncols * WD + col * WD + k] = a[WD + k]; }
@@ -82,15 +106,17 @@ extern "C" int pspace_cuda_moments(const pspace_ctx *c, long long q0, long long 
   PS_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
   const long long nq = q1 - q0;
-  const int ctiles = (ncols + MT_X - 1) / MT_X;
-  int slices = (int)std::max<long long>(1, std::min<long long>((148LL * 8 + ctiles - 1) / ctiles, (nq + 63) / 64));
+  const int ct = ncols < MT_COLS ? ncols : MT_COLS;          // column tile; R = 256/ct rows per step
+  const int ctiles = (ncols + ct - 1) / ct;
+  const long long rows_per_step = MT / ct;
+  int slices = (int)std::max<long long>(1, std::min<long long>((148LL * 8 + ctiles - 1) / ctiles, (nq + 16 * rows_per_step - 1) / (16 * rows_per_step)));
   const long long rows_per_slice = (nq + slices - 1) / slices;
   slices = (int)((nq + rows_per_slice - 1) / rows_per_slice);
   double *part = nullptr;
   PS_CUDA(cudaMallocAsync(&part, sizeof(double) * (size_t)slices * 2 * ncols * c->width, st));
   dim3 grid(slices, ctiles);
-  if (c->is_complex) k_moments_partial<true><<<grid, MT_X * MT_Y, 0, st>>>(d_f, c->d_W, q0, nq, ncols, rows_per_slice, part);
-  else k_moments_partial<false><<<grid, MT_X * MT_Y, 0, st>>>(d_f, c->d_W, q0, nq, ncols, rows_per_slice, part);
+  if (c->is_complex) k_moments_partial<true><<<grid, MT, 0, st>>>(d_f, c->d_W, q0, nq, ncols, ct, rows_per_slice, part);
+  else k_moments_partial<false><<<grid, MT, 0, st>>>(d_f, c->d_W, q0, nq, ncols, ct, rows_per_slice, part);
   PS_LAUNCH_CHECK(c);
   if (c->is_complex) k_moments_final<true><<<(ncols + 127) / 128, 128, 0, st>>>(part, slices, ncols, d_mean, d_second, d_var);
   else k_moments_final<false><<<(ncols + 127) / 128, 128, 0, st>>>(part, slices, ncols, d_mean, d_second, d_var);

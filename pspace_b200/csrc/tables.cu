@@ -85,23 +85,25 @@ __global__ void k_grid_digits_weights(GridParams g, long long Q, const double *w
   if (g.DP == 32) dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
 }
 
-// materialised grid columns: Z,Y [q1-q0][nvars] point-major, W [q1-q0]  (what quadrature(q,zq,yq) hands out)
+// materialised grid columns: Z,Y [q1-q0][nvars] point-major, W [q1-q0]  (what quadrature(q,zq,yq) hands out).
+// One thread per (point, variable) element so that consecutive threads write consecutive addresses.
 template <typename S>
 __global__ void k_tensor_grid(GridParams g, long long q0, long long q1, const double *zp, const double *yp,
-                              const double *wp, double *Z, double *Y, double *W) {
+                              const double *wp, const uint8_t *qdig, double *Z, double *Y, double *W) {
   typedef scalar_of<S> SO;
-  long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (q0 + r >= q1) return;
-  int dig[PSPACE_MAX_VARS];
-  digits_of(g, q0 + r, dig);
-  if (W) {
-    S w = SO::load(wp, g.roff[0] + dig[0]);
-    for (int d = 1; d < g.nvars; d++) w = s_mul(w, SO::load(wp, g.roff[d] + dig[d]));
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long n = q1 - q0;
+  if (e >= n * g.nvars) return;
+  const long long r = e / g.nvars;
+  const int d = (int)(e % g.nvars);
+  const uint8_t *dg = qdig + (q0 + r) * g.DP;
+  const int o = g.roff[d] + dg[d];
+  if (Z) SO::store(Z, e, SO::load(zp, o));
+  if (Y) SO::store(Y, e, SO::load(yp, o));
+  if (W && d == 0) {
+    S w = SO::load(wp, g.roff[0] + dg[0]);
+    for (int k = 1; k < g.nvars; k++) w = s_mul(w, SO::load(wp, g.roff[k] + dg[k]));
     SO::store(W, r, w);
-  }
-  for (int d = 0; d < g.nvars; d++) {
-    if (Z) SO::store(Z, r * g.nvars + d, SO::load(zp, g.roff[d] + dig[d]));
-    if (Y) SO::store(Y, r * g.nvars + d, SO::load(yp, g.roff[d] + dig[d]));
   }
 }
 
@@ -130,12 +132,30 @@ __global__ void __launch_bounds__(EB_WARPS * 32) k_eval_basis_grid(GridParams g,
   const long long nqr = q1 - q0;
   long long r = (blockIdx.x * (long long)EB_WARPS + warp) * 32 + lane;
   if (r >= nqr) return;
+  // table offset of (variable d, my point's digit) in my own shared-memory slot: dynamic indexing without local memory
+  unsigned short *mybase = reinterpret_cast<unsigned short *>(rowoff + EB_KB * g.nvars) + threadIdx.x * PSPACE_MAX_VARS;
   const uint8_t *dg = qdig + (q0 + r) * g.DP;
-  int dig[PSPACE_MAX_VARS];
-  for (int d = 0; d < g.nvars; d++) dig[d] = dg[d];
-  for (int kk = 0; kk < EB_KB && kb0 + kk < k1; kk++) {
+  for (int d = 0; d < g.nvars; d++) mybase[d] = (unsigned short)dg[d];
+  const int nk = min(EB_KB, k1 - kb0);
+  int kk = 0;
+  for (; kk + 4 <= nk; kk += 4) {                      // four independent product chains
+    S v0 = SO::from(1.0), v1 = v0, v2 = v0, v3 = v0;
+    const int *ro = rowoff + kk * g.nvars;
+    for (int d = 0; d < g.nvars; d++) {
+      const int dd = mybase[d];
+      v0 = s_mul(v0, SO::load(Ts, ro[d] + dd));
+      v1 = s_mul(v1, SO::load(Ts, ro[g.nvars + d] + dd));
+      v2 = s_mul(v2, SO::load(Ts, ro[2 * g.nvars + d] + dd));
+      v3 = s_mul(v3, SO::load(Ts, ro[3 * g.nvars + d] + dd));
+    }
+    SO::store(psi, (size_t)(kb0 + kk - k0) * nqr + r, v0);
+    SO::store(psi, (size_t)(kb0 + kk + 1 - k0) * nqr + r, v1);
+    SO::store(psi, (size_t)(kb0 + kk + 2 - k0) * nqr + r, v2);
+    SO::store(psi, (size_t)(kb0 + kk + 3 - k0) * nqr + r, v3);
+  }
+  for (; kk < nk; kk++) {
     S v = SO::from(1.0);
-    for (int d = 0; d < g.nvars; d++) v = s_mul(v, SO::load(Ts, rowoff[kk * g.nvars + d] + dig[d]));
+    for (int d = 0; d < g.nvars; d++) v = s_mul(v, SO::load(Ts, rowoff[kk * g.nvars + d] + mybase[d]));
     SO::store(psi, (size_t)(kb0 + kk - k0) * nqr + r, v);
   }
 }
@@ -236,9 +256,9 @@ int ps_tensor_grid(const pspace_ctx *c, long long q0, long long q1, double *Z, d
   if (q1 <= q0) return PSPACE_OK;
   GridParams g;
   fill_grid(c, g);
-  unsigned nb = (unsigned)((q1 - q0 + 255) / 256);
-  if (c->is_complex) k_tensor_grid<cplx><<<nb, 256, 0, st>>>(g, q0, q1, c->d_zp, c->d_yp, c->d_wp, Z, Y, W);
-  else k_tensor_grid<double><<<nb, 256, 0, st>>>(g, q0, q1, c->d_zp, c->d_yp, c->d_wp, Z, Y, W);
+  unsigned nb = (unsigned)(((q1 - q0) * c->nvars + 255) / 256);
+  if (c->is_complex) k_tensor_grid<cplx><<<nb, 256, 0, st>>>(g, q0, q1, c->d_zp, c->d_yp, c->d_wp, c->d_qdig, Z, Y, W);
+  else k_tensor_grid<double><<<nb, 256, 0, st>>>(g, q0, q1, c->d_zp, c->d_yp, c->d_wp, c->d_qdig, Z, Y, W);
   PS_LAUNCH_CHECK(c);
   return PSPACE_OK;
 }
@@ -251,7 +271,7 @@ int ps_eval_basis_grid(const pspace_ctx *c, int k0, int k1, long long q0, long l
   PS_CUDA(cudaMallocAsync(&d_toff, sizeof(int) * c->nvars, st));
   PS_CUDA(cudaMemcpyAsync(d_toff, c->toff, sizeof(int) * c->nvars, cudaMemcpyHostToDevice, st));
   dim3 grid((unsigned)((q1 - q0 + EB_WARPS * 32 - 1) / (EB_WARPS * 32)), (unsigned)((k1 - k0 + EB_KB - 1) / EB_KB));
-  size_t smem = sizeof(double) * c->width * c->tsz + sizeof(int) * EB_KB * c->nvars;
+  size_t smem = sizeof(double) * c->width * c->tsz + sizeof(int) * EB_KB * c->nvars + sizeof(unsigned short) * EB_WARPS * 32 * PSPACE_MAX_VARS;
   if (c->is_complex) {
     PS_CUDA(cudaFuncSetAttribute(k_eval_basis_grid<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_eval_basis_grid<cplx><<<grid, EB_WARPS * 32, smem, st>>>(g, c->tsz, c->d_T, d_toff, c->d_deg, k0, k1, q0, q1, c->d_qdig, psi);
