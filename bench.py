@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sym", action="store_true")
+    ap.add_argument("--ref-seconds", type=float, default=0.0, help="--impl reference: seconds per step (0 = derive from --steps)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of the CPU baseline sample")
     return ap.parse_args()
 
@@ -153,7 +154,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     w = workload(args.workload)
-    per_step = max(5.0, min(30.0, 120.0 / max(1, args.steps + args.warmup)))
+    per_step = args.ref_seconds if args.ref_seconds > 0 else max(5.0, min(30.0, 120.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         cpu_sample(w, min(per_step, 5.0))
     vals, info = [], None

@@ -134,6 +134,12 @@ int pspace_cuda_project_vector(const pspace_ctx *ctx, const pspace_project_args 
                                double *d_F, void *d_workspace, size_t workspace_bytes, void *stream);
 int pspace_cuda_project_matrix(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_J,
                                double *d_C, void *d_workspace, size_t workspace_bytes, void *stream);
+/* Many elements sharing one container (BASELINE.json configs[2]: "24x24 element Jacobians over 10k elements"): element e
+ * reads d_J + e*j_elem_stride and writes d_C + e*c_elem_stride (strides in scalars); same window / q-range / workspace
+ * for all.  The basis panels are built for the first element and reused. */
+int pspace_cuda_project_matrix_batched(const pspace_ctx *ctx, const pspace_project_args *a, int nelem, const double *d_J,
+                                       long long j_elem_stride, double *d_C, long long c_elem_stride, void *d_workspace,
+                                       size_t workspace_bytes, void *stream);
 /* Host-buffer forms (the call a host-side user of the reference makes: pageable or pinned host
  * arrays in, host array out; H2D + kernels + D2H inside, synchronous). */
 int pspace_cuda_project_vector_host(pspace_ctx *ctx, const pspace_project_args *a, const double *h_f, double *h_F);

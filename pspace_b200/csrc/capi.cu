@@ -245,6 +245,25 @@ int pspace_cuda_evaluate_expansion(const pspace_ctx *c, int k0, int k1, long lon
   return ps_expand(c, k0, k1, q0, q1, ncols, accumulate, d_V, d_U, (cudaStream_t)stream);
 }
 
+int pspace_cuda_project_matrix_batched(const pspace_ctx *c, const pspace_project_args *a, int nelem, const double *d_J,
+                                       long long j_elem_stride, double *d_C, long long c_elem_stride, void *d_ws,
+                                       size_t ws_bytes, void *stream) {
+  if (!c || !a || nelem < 0) return ps_fail(PSPACE_EINVAL, "bad argument");
+  if (nelem > 0 && (!d_J || !d_C)) return ps_fail(PSPACE_EINVAL, "null buffer");
+  PS_CUDA(cudaSetDevice(c->device));
+  pspace_ctx *mc = const_cast<pspace_ctx *>(c);
+  const int saved = mc->panel_cache;
+  int rc = PSPACE_OK;
+  for (int e = 0; e < nelem && rc == PSPACE_OK; e++) {
+    if (e == 1) mc->panel_cache = 1;          // elements share the container: the basis panels are built once
+    rc = ps_project(c, 1, a, d_J + (size_t)e * j_elem_stride * c->width, d_C + (size_t)e * c_elem_stride * c->width, d_ws,
+                    ws_bytes, (cudaStream_t)stream);
+  }
+  mc->panel_cache = saved;
+  if (!saved) mc->panel_valid = false;
+  return rc;
+}
+
 static int ensure(void **buf, size_t *have, size_t need) {
   if (need <= *have) return PSPACE_OK;
   if (*buf) { PS_CUDA(cudaFree(*buf)); *buf = nullptr; *have = 0; }

@@ -196,6 +196,23 @@ class DeviceContainer:
                                                     ws.data_ptr() if ws is not None else None, need, _stream_ptr()))
         return out
 
+    def projectMatrixBatched(self, J, i0=0, i1=None, j0=0, j1=None, q0=0, q1=None, out=None):
+        """Elements sharing this container: J device [E][q1-q0][m2] -> C [E][i1-i0][j1-j0][m2] (panels built once)."""
+        i1 = self.N if i1 is None else i1
+        j1 = self.N if j1 is None else j1
+        q1 = self.Q if q1 is None else q1
+        assert J.is_cuda and J.dtype == self.t_dtype and J.is_contiguous() and J.dim() == 3 and J.shape[1] == q1 - q0
+        E, _, m2 = J.shape
+        if out is None:
+            out = torch.empty((E, i1 - i0, j1 - j0, m2), dtype=self.t_dtype, device=self.device)
+        a = self._args(i0, i1, j0, j1, q0, q1, m2, False, 0, 0)
+        ws, need = self._workspace(1, a)
+        with torch.cuda.device(self.device):
+            check(self.L.pspace_cuda_project_matrix_batched(self.h, ctypes.byref(a), E, J.data_ptr(), (q1 - q0) * m2, out.data_ptr(),
+                                                            (i1 - i0) * (j1 - j0) * m2, ws.data_ptr() if ws is not None else None,
+                                                            need, _stream_ptr()))
+        return out
+
     def projectMatrixHost(self, J, i0=0, i1=None, j0=0, j1=None, q0=0, q1=None, out=None, accumulate=False):
         """Host-buffer form (numpy or pinned torch CPU tensors in/out); copies are inside the call (J rows q0..q1-1)."""
         i1 = self.N if i1 is None else i1

@@ -487,6 +487,26 @@ def test_edge_shapes_vs_oracle(case):
     c.close()
 
 
+def test_batched_elements_share_one_container():
+    """configs[2] shape: several elements' 24x24 Jacobians over one 4-parameter tensor container (degree lowered so the
+    oracle finishes in seconds); the panels are built once and each element equals its own projection."""
+    from pspace_b200.workloads import mixed_params
+    rng = np.random.default_rng(111)
+    ps = mixed_params(4, 2)                                                # N = Q = 81
+    o = H.CpuContainer(H.oracle_api(False), ps, 0).initialize()
+    c = _dc(ps, 0, False).initialize()
+    E, m2 = 5, 576
+    J = rng.normal(size=(E, o.Q, m2))
+    C = c.projectMatrixBatched(torch.from_numpy(J).cuda(), 3, 30, 0, o.N)
+    launches0 = c.launchCount()
+    c.projectMatrixBatched(torch.from_numpy(J).cuda(), 3, 30, 0, o.N)
+    per_call = c.launchCount() - launches0
+    assert per_call <= 2 + 2 * E                                           # 2 panel kernels once + (project, fix-up) per element
+    for e in range(E):
+        assert normwise(C[e].cpu().numpy(), o.project_matrix(J[e], 3, 30, 0, o.N, nthreads=8)) < TOL, e
+    c.close()
+
+
 def test_no_write_outside_the_output_window():
     """compute-sanitizer is closed on this pool: own bounds check.  The output sits inside a larger buffer of
     sentinels; every kernel path (TMA stream-K incl. fix-up, generic incl. split reduce, vector) must leave the

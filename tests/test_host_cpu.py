@@ -134,3 +134,23 @@ def test_workload_sizes_match_survey_table():
     sizes = {k: (f().N, f().Q, f().m) for k, f in WL.ALL.items()}
     assert sizes == {1: (64, 64, 1), 2: (126, 3125, 8), 3: (1296, 1296, 24), 4: (65536, 65536, 24), 5: (286, 1048576, 24)}
     assert WL.cfg4().complex_ and WL.cfg5().seed == 20265
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """`bench.py --impl reference` (CPU arm of the driver's comparison) on the small cfg2 workload, shortened."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg2", "--steps", "1",
+                        "--warmup", "0", "--ref-seconds", "0.3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "updates/s" and line["value"] > 1e5
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    # rank != 0 under torchrun exits silently
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
+                        text=True, timeout=60, env=env)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
