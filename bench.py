@@ -372,6 +372,11 @@ def run_b200(args):
 
 def main():
     args = parse()
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # the driver launches N > 1 through torch.distributed.run; do the same when invoked directly
+        port = 29500 + (os.getpid() % 2000)
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
