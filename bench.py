@@ -260,6 +260,41 @@ def run_b200(args):
     ms_per_step = total_ms / args.steps
     value = updates / (ms_per_step * 1e-3)
 
+    # ---- vector (residual-type) projection of the same container, m = block edge (SURVEY.md §8d asks for it beside) ------
+    fvec = J[:, : w.m].contiguous()
+    Fv = torch.empty((N, w.m), dtype=tdt, device=dev)
+
+    def vec_step():
+        c.projectVector(fvec, q0=q0, q1=q1, out=Fv)
+        if world > 1:
+            dist.all_reduce(torch.view_as_real(Fv) if w.complex_ else Fv, op=dist.ReduceOp.SUM)
+    vec_step()
+    barrier()
+    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    v0.record()
+    for _ in range(10):
+        vec_step()
+    v1.record()
+    barrier()
+    vt = torch.tensor([v0.elapsed_time(v1) / 10], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vt, op=dist.ReduceOp.MAX)
+    vector = {"value": float(N) * Q / (float(vt.item()) * 1e-3), "unit": "(k,q) updates/s of m FMAs", "ms_per_step": float(vt.item()),
+              "m": w.m, "note": "F[k][:] = sum_q w_q psi_k(z_q) f[q][:], all N basis rows, all q; f = first m columns of J"}
+
+    # ---- live parity of this run's kernels against the CPU oracle: a 2x2 pair window over rank 0's first 32768 points ----
+    parity = None
+    if rank == 0:
+        import numpy as np
+        from oracle import harness as H
+        o = H.CpuContainer(H.oracle_api(w.complex_), w.params, w.basis_type).initialize()
+        qa, qb = q0, min(q1, q0 + 32768)
+        ia, ja = N // 2, max(0, N - 2)
+        got = c.projectMatrix(J[: qb - qa].contiguous(), ia, ia + 2, ja, ja + 2, q0=qa, q1=qb).cpu().numpy()
+        ref = o.project_matrix_qrange(J[: qb - qa].cpu().numpy(), qa, qb, ia, ia + 2, ja, ja + 2, nthreads=2)
+        parity = {"normwise_err": float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))), "tolerance": 1e-12,
+                  "window": f"pairs i in [{ia},{ia + 2}) x j in [{ja},{ja + 2}), q in [{qa},{qb}), all {m2} columns, vs the oracle's (i,j,q) loop"}
+
     # ---- optional: the same full window with the i<->j symmetry exploited (reported separately) ----
     sym = None
     if wi == wj and not args.no_sym:
@@ -358,6 +393,8 @@ def run_b200(args):
                        "l2": f"inputs larger than L2: J shard {nq * m2 * width * 8 / 1e9:.2f} GB + C {wi * wj * m2 * width * 8 / 1e9:.2f} GB vs 126 MB L2 (no flush needed)",
                        "plan": plan, "panel_cache": 0},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}
+    line["vector_projection"] = vector
+    line["parity"] = parity
     if sym:
         line["symmetric"] = sym
     if e2e:

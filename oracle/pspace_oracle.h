@@ -1,7 +1,8 @@
 /* TEST INFRASTRUCTURE — CPU restatement ("oracle") of the pspace stochastic Galerkin hot path.
  *
- * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
- * load this library, and only as the checker / CPU baseline.  The product path (libpspace_cuda.so,
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / parity / --impl reference legs (plus the
+ * developer scripts under tools/ that generate fixtures or time the CPU side) may load this library, and only as the
+ * checker / CPU baseline.  The product path (libpspace_cuda.so,
  * libpspace.so, pspace_b200/) never links, imports or calls it.
  *
  * Parity status: PINNED.  Every function is checked bit for bit against the compiled, unmodified

@@ -3,28 +3,28 @@
 //   matrix:  C[i][j][c] = sum_q (w_q psi_i(z_q) psi_j(z_q)) J[q][c]      TACSStochasticElement.cpp:380-414
 //   vector:  F[k][c]    = sum_q (w_q psi_k(z_q)) f[q][c]                 TACSStochasticElement.cpp:283-311
 //
-// i.e. the dense contraction (N^2 x Q).(Q x m^2) with a GENERATED left operand.  The reference evaluates
-// it as N^2*Q scalar calls of basis()/quadrature(); here it is one FP64 tensor-core GEMM:
+// i.e. the dense contraction (N^2 x Q).(Q x m^2) with a GENERATED left operand.  The reference evaluates it as
+// N^2*Q scalar calls of basis()/quadrature(); here it is one FP64 tensor-core GEMM.  Common to both kernels below:
 //
-//  * math: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  Measured on this B200 (profiles/r01_fp64_peak.md):
-//    DMMA sustains 37.0 TFLOP/s = 99.5 % of 148 SM x 64 FMA/clk x 1.965 GHz, the DFMA pipe 33.5 — both
-//    issue to the same FP64 pipe (mixing them adds nothing), DMMA needs 1/8 of the issue slots and no
-//    per-FMA operand fetch, so DMMA it is.  tcgen05 has no FP64 kind.
-//  * right operand J[q][c]: streamed from HBM/L2 once per CTA tile with 16-byte cp.async (LDGSTS) into a
-//    STAGES-deep shared-memory ring, row pitch BN+4 doubles so the DMMA B-fragment reads
-//    (k = lane%4, n = lane/4) hit 16 distinct banks.
-//  * left operand: never materialised.  A CTA tile is BI basis rows i x 8 basis rows j (= BM = 8*BI
-//    ordered pairs); per chunk of KQ=32 quadrature points the CTA stages psi_i(z_q) (BI x KQ) and
-//    w_q psi_j(z_q) (8 x KQ) in shared memory as products of the 1-D tables T_d[alpha][i_d] (also in
-//    shared memory) selected by the mixed-radix digits of q, in the reference's product order
-//    (ParameterContainer.cpp:184-192).  Each lane then forms its A-fragment element
-//    a[row=(i,j)][k=q] = psi_i(q) * (w_q psi_j(q)) with ONE DMUL that feeds WN DMMAs.
-//  * USE_COMPLEX: J, psi and C are interleaved (re,im); C = A_re*[B] + A_im*[B'] with
-//    B'[k][2c] = -B[k][2c+1], B'[k][2c+1] = B[k][2c]  (4 real FMAs per complex FMA, naive complex multiply
-//    so complex-step imaginary parts survive).
-//  * q-range [q0,q1) is a call argument (multi-GPU shard) and is further cut into `ksplit` slices over
-//    blockIdx.y; slices write partial tiles to a workspace that a second kernel sums in slice order
-//    (deterministic — no atomics).
+//  * math: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  Measured on this B200 (profiles/r01_fp64_peak.md): DMMA sustains
+//    37.0 TFLOP/s = 99.5 % of 148 SM x 64 FMA/clk x 1.965 GHz, the DFMA pipe 33.5; both are served by the same FP64
+//    datapath (mixing them adds nothing), DMMA needs 1/8 of the issue slots, so DMMA it is.  tcgen05 has no FP64 kind.
+//  * a CTA tile is BI basis rows i x 8 basis rows j (= BM = 8*BI ordered pairs) x BN real columns; each lane forms its
+//    A-fragment element a[row=(i,j)][k=q] = psi_i(q) * (w_q psi_j(q)) with ONE DMUL that feeds WN DMMAs — the pair
+//    products (N^2 x Q) are never materialised.
+//  * shared-memory tiles have a pitch == 4 (mod 16) doubles so the DMMA fragment reads (k = lane%4, n = lane/4) hit
+//    16 distinct banks per half-warp.
+//  * USE_COMPLEX: J, psi and C are interleaved (re,im); C = A_re*[B] + A_im*[B'] with B'[k][2c] = -B[k][2c+1],
+//    B'[k][2c+1] = B[k][2c]  (4 real FMAs per complex FMA, naive complex multiply so complex-step imaginary parts survive).
+//  * the q-range [q0,q1) is a call argument (multi-GPU shard / upload slab).
+//
+// k_project_ws (fast path, TMA-addressable operands): persistent, warp-specialised, TMA + mbarrier; psi comes from basis
+//   panels written once per call by k_psi_panel; work = data-parallel full waves + stream-K remainder + k_fixup.  See the
+//   comment block above it.
+// k_project (generic path: odd column counts / unaligned operands): all 8 warps stage psi in-kernel per 32-point chunk as
+//   products of the shared-memory 1-D tables T_d[alpha][i_d] selected by the mixed-radix digits of q (reference product
+//   order, ParameterContainer.cpp:184-192), J streams in with 16/8-byte cp.async (LDGSTS) through a STAGES-deep ring;
+//   the q-range is cut into `ksplit` slices over blockIdx.y whose partial windows k_reduce_slices adds in slice order.
 #include "ctx.h"
 #include <algorithm>
 #include <cuda.h>

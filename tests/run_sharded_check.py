@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Multi-GPU parity check (run under torchrun on N GPUs of one box):
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/check_sharded.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/run_sharded_check.py
 
 Every rank projects its quadrature-point shard of cfg2 (real) and of a complex 4-parameter container with the CUDA
 path; the partial blocks are combined with NCCL (allreduce and reduce-scatter) and compared on rank 0 with the CPU
