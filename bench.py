@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sym", action="store_true")
+    ap.add_argument("--collective", default="nccl", choices=["nccl", "peer"],
+                    help="N > 1: how the partial coefficient blocks are combined in the timed step: one NCCL allreduce after the kernel "
+                         "(default: measured faster), or the fused peer-memory exchange (pushes from the projection epilogue); the other "
+                         "one is timed beside it")
     ap.add_argument("--ref-seconds", type=float, default=0.0, help="--impl reference: seconds per step (0 = derive from --steps)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of the CPU baseline sample")
     return ap.parse_args()
@@ -214,10 +218,39 @@ def run_b200(args):
     C = torch.empty((wi, wj, m2), dtype=tdt, device=dev)
     Cr = torch.view_as_real(C) if w.complex_ else C
 
-    def step():
+    # N > 1: the exchange of the partial coefficient blocks is fused into the kernels (peer-memory pushes from the
+    # projection epilogue + reduce/all-gather kernel, pspace_b200/fused.py); the plain NCCL allreduce path is timed beside it.
+    fp, fused_note = None, None
+    if world > 1:
+        try:
+            from pspace_b200.fused import FusedShardedProjector
+            fp = FusedShardedProjector(c, 0, wi, 0, wj, ncols=m2)
+        except Exception as e:                      # no peer access / symmetric memory unavailable: NCCL path only
+            fp, fused_note = None, f"fused peer path unavailable ({type(e).__name__}: {e}); NCCL allreduce used"
+    ok = torch.tensor([1 if fp is not None else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            fp = None
+
+    def nccl_step():
         c.projectMatrix(J, 0, wi, 0, wj, q0=q0, q1=q1, out=C)
         if world > 1:
             dist.all_reduce(Cr, op=dist.ReduceOp.SUM)
+
+    def project_only():
+        if fp is not None:
+            fp.projectMatrix(J)
+        else:
+            c.projectMatrix(J, 0, wi, 0, wj, q0=q0, q1=q1, out=C)
+
+    use_peer = fp is not None and args.collective == "peer"
+
+    def step():
+        if use_peer:
+            fp.projectMatrix(J)
+        else:
+            nccl_step()
 
     updates = float(wi) * wj * Q                                   # all ordered pairs of the window x all q
     flop_per_update = m2 * (8 if w.complex_ else 2)
@@ -239,18 +272,19 @@ def run_b200(args):
     ev[0].record()
     kern_ms = []
     for s in range(args.steps):
-        a, b = ev[2 + 2 * s], ev[3 + 2 * s]
-        a.record()
-        c.projectMatrix(J, 0, wi, 0, wj, q0=q0, q1=q1, out=C)
-        b.record()
-        if world > 1:
-            dist.all_reduce(Cr, op=dist.ReduceOp.SUM)
+        a, b = ev[2 + 2 * s], ev[3 + 2 * s]        # events around this rank's projection kernels only (roofline)
+        if use_peer:
+            fp.projectMatrix(J, a, b)
+        else:
+            a.record()
+            c.projectMatrix(J, 0, wi, 0, wj, q0=q0, q1=q1, out=C)
+            b.record()
+            if world > 1:
+                dist.all_reduce(Cr, op=dist.ReduceOp.SUM)
     ev[1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[1])
-    for s in range(args.steps):
-        kern_ms.append(ev[2 + 2 * s].elapsed_time(ev[3 + 2 * s]))
     launches = c.launchCount() - launches0
     plan = c.lastPlan()
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -259,6 +293,31 @@ def run_b200(args):
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     value = updates / (ms_per_step * 1e-3)
+
+    for s in range(args.steps):
+        kern_ms.append(ev[2 + 2 * s].elapsed_time(ev[3 + 2 * s]))
+    # N > 1: the same step with the exchange done by NCCL, timed beside
+    other = None
+    if world > 1 and fp is not None:
+        alt = nccl_step if use_peer else (lambda: fp.projectMatrix(J))
+        alt()
+        barrier()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for _ in range(args.steps):
+            alt()
+        n1.record()
+        barrier()
+        nt = torch.tensor([n0.elapsed_time(n1) / args.steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(nt, op=dist.ReduceOp.MAX)
+        nccl_step()
+        fp.projectMatrix(J)
+        diff = float((fp.out - C).abs().max() / C.abs().max())
+        other = {"collective": "nccl allreduce after the kernel" if use_peer else
+                               "fused: partial tiles pushed to their owner rank over NVLink from the projection epilogue (peer-mapped "
+                               "symmetric memory), then k_peer_reduce_gather (pspace_b200/fused.py)",
+                 "ms_per_step": float(nt.item()), "value": updates / (float(nt.item()) * 1e-3), "unit": UNIT,
+                 "max_rel_diff_between_the_two": diff}
 
     # ---- vector (residual-type) projection of the same container, m = block edge (SURVEY.md §8d asks for it beside) ------
     fvec = J[:, : w.m].contiguous()
@@ -389,10 +448,15 @@ def run_b200(args):
             "config": {"workload": f"{w.name}: matrix (Jacobian) projection, all ordered pairs of a {wi}x{wj} basis window x all q",
                        "N": N, "Q": Q, "m": w.m, "params": w.nvars, "basis": "complete" if w.basis_type else "tensor",
                        "updates_per_step": updates, "flop_per_step": updates * flop_per_update,
-                       "parallelism": f"q-shard x{world}" + (" + NCCL allreduce of C" if world > 1 else ""),
+                       "parallelism": f"q-shard x{world}" + ((" + fused peer-memory reduce-scatter/all-gather of C (NVLink pushes from the projection epilogue)"
+                                                               if use_peer else " + NCCL allreduce of C") if world > 1 else ""),
                        "l2": f"inputs larger than L2: J shard {nq * m2 * width * 8 / 1e9:.2f} GB + C {wi * wj * m2 * width * 8 / 1e9:.2f} GB vs 126 MB L2 (no flush needed)",
                        "plan": plan, "panel_cache": 0},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}
+    if other:
+        line["other_collective"] = other
+    if fused_note:
+        line["config"]["fused_note"] = fused_note
     line["vector_projection"] = vector
     line["parity"] = parity
     if sym:

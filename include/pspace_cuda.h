@@ -32,6 +32,7 @@ extern "C" {
 #define PSPACE_ESTATE (-3)   /* call out of order (e.g. project before initialize) */
 #define PSPACE_ENOMEM (-4)
 #define PSPACE_MAX_VARS 32
+#define PSPACE_MAX_PEERS 16  /* ranks of the fused multi-GPU exchange */
 #define PSPACE_MAX_NQ 20     /* 1-D rules exist for npoints 1..20 (GaussianQuadrature.cpp:31-1483) */
 
 /* parameter kinds = the three ParameterFactory products (src/include/ParameterFactory.h:21-28) */
@@ -148,6 +149,24 @@ int pspace_cuda_project_matrix_host(pspace_ctx *ctx, const pspace_project_args *
  * (multi-GPU allreduce) before reading it back.  The host forms upload J in slabs of quadrature points through a
  * double buffer, overlapping the upload of slab s+1 with the projection of slab s (option "slab_mb"). */
 int pspace_cuda_project_matrix_hostin(pspace_ctx *ctx, const pspace_project_args *a, const double *h_J, double *d_C);
+
+/* ---- fused multi-GPU projection: compute + reduce-scatter/all-gather over peer-mapped memory (NVLink) -----------------
+ * Each rank projects its quadrature-point shard; instead of keeping a full partial C and calling a collective, every
+ * finished partial TILE is pushed by the projection kernel's epilogue straight into the receive slot of the rank that
+ * owns the tile (peer stores, overlapped with the math of the following tiles).  After a cross-rank barrier,
+ * pspace_cuda_peer_reduce_gather adds the `world` partial blocks of each owned element in rank order (deterministic)
+ * and stores the total into the C window of every rank.  The caller supplies peer-mapped buffers (e.g.
+ * torch.distributed._symmetric_memory) and the two barriers:
+ *     project_matrix_peer  ->  barrier  ->  peer_reduce_gather  ->  barrier
+ * peer_recv[w] / peer_out[w] are HOST arrays of `world` device pointers (rank w's receive buffer / C window as mapped
+ * into this process).  pspace_cuda_peer_layout gives the receive-buffer size in doubles.  Restrictions: matrix mode,
+ * no mask / symmetric / accumulate, even number of real columns (TMA path). */
+int pspace_cuda_peer_layout(const pspace_ctx *ctx, const pspace_project_args *a, int world, long long *recv_doubles);
+int pspace_cuda_project_matrix_peer(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_J,
+                                    double *const *peer_recv, int world, int rank, void *d_workspace,
+                                    size_t workspace_bytes, void *stream);
+int pspace_cuda_peer_reduce_gather(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_recv_local,
+                                   double *const *peer_out, int world, int rank, void *stream);
 
 /* ---- (f1) polynomial-chaos expansion evaluated at quadrature points -------------------------------------
  * U[q][c] = sum_{k in [k0,k1)} psi_k(z_q) V[k-k0][c]  for q in [q0,q1);  d_V[(k1-k0)][ncols], d_U[(q1-q0)][ncols]

@@ -57,6 +57,9 @@ SIGNATURES = {
     "pspace_cuda_project_workspace": (_sz, [_vp, _i, ctypes.POINTER(ProjectArgs)]),
     "pspace_cuda_project_vector": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _vp, _sz, _vp]),
     "pspace_cuda_project_matrix": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _vp, _sz, _vp]),
+    "pspace_cuda_peer_layout": (_i, [_vp, ctypes.POINTER(ProjectArgs), _i, ctypes.POINTER(_ll)]),
+    "pspace_cuda_project_matrix_peer": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _i, _i, _vp, _sz, _vp]),
+    "pspace_cuda_peer_reduce_gather": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _i, _i, _vp]),
     "pspace_cuda_project_matrix_batched": (_i, [_vp, ctypes.POINTER(ProjectArgs), _i, _vp, _ll, _vp, _ll, _vp, _sz, _vp]),
     "pspace_cuda_project_vector_host": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp]),
     "pspace_cuda_project_matrix_host": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp]),

@@ -245,6 +245,28 @@ int pspace_cuda_evaluate_expansion(const pspace_ctx *c, int k0, int k1, long lon
   return ps_expand(c, k0, k1, q0, q1, ncols, accumulate, d_V, d_U, (cudaStream_t)stream);
 }
 
+int pspace_cuda_peer_layout(const pspace_ctx *c, const pspace_project_args *a, int world, long long *recv_doubles) {
+  if (!c || !a || !recv_doubles) return ps_fail(PSPACE_EINVAL, "null argument");
+  return ps_peer_layout(c, a, world, recv_doubles);
+}
+int pspace_cuda_project_matrix_peer(const pspace_ctx *c, const pspace_project_args *a, const double *d_J,
+                                    double *const *peer_recv, int world, int rank, void *d_ws, size_t ws_bytes, void *stream) {
+  if (!c || !a || !d_J || !peer_recv) return ps_fail(PSPACE_EINVAL, "null argument");
+  if (world < 1 || world > PSPACE_MAX_PEERS || rank < 0 || rank >= world) return ps_fail(PSPACE_EINVAL, "world/rank");
+  PS_CUDA(cudaSetDevice(c->device));
+  PeerInfo pi;
+  pi.world = world; pi.rank = rank;
+  for (int w = 0; w < PSPACE_MAX_PEERS; w++) pi.recv[w] = w < world ? peer_recv[w] : nullptr;
+  return ps_project_ex(c, 1, a, d_J, nullptr, d_ws, ws_bytes, (cudaStream_t)stream, &pi);
+}
+int pspace_cuda_peer_reduce_gather(const pspace_ctx *c, const pspace_project_args *a, const double *d_recv_local,
+                                   double *const *peer_out, int world, int rank, void *stream) {
+  if (!c || !a || !d_recv_local || !peer_out) return ps_fail(PSPACE_EINVAL, "null argument");
+  if (world < 1 || world > PSPACE_MAX_PEERS || rank < 0 || rank >= world) return ps_fail(PSPACE_EINVAL, "world/rank");
+  PS_CUDA(cudaSetDevice(c->device));
+  return ps_peer_reduce_gather(c, a, d_recv_local, peer_out, world, rank, (cudaStream_t)stream);
+}
+
 int pspace_cuda_project_matrix_batched(const pspace_ctx *c, const pspace_project_args *a, int nelem, const double *d_J,
                                        long long j_elem_stride, double *d_C, long long c_elem_stride, void *d_ws,
                                        size_t ws_bytes, void *stream) {

@@ -6,6 +6,12 @@
 #include <vector>
 #include "../../include/pspace_cuda.h"
 
+// multi-GPU fused projection: the peer-mapped receive buffers of all ranks (project.cu, EPI_PEER)
+struct PeerInfo {
+  int world, rank;
+  double *recv[PSPACE_MAX_PEERS];
+};
+
 struct pspace_ctx {
   int device = 0, is_complex = 0, nvars = 0, basis_type = 0, width = 1;  // width = doubles per scalar
   int kinds[PSPACE_MAX_VARS] = {0}, dmax[PSPACE_MAX_VARS] = {0};
@@ -72,3 +78,8 @@ int ps_expand(const pspace_ctx *c, int k0, int k1, long long q0, long long q1, i
               const double *d_V, double *d_U, cudaStream_t st);
 int ps_project(const pspace_ctx *ctx, int is_matrix, const pspace_project_args *a, const double *d_in, double *d_out,
                void *d_ws, size_t ws_bytes, cudaStream_t st);
+int ps_project_ex(const pspace_ctx *ctx, int is_matrix, const pspace_project_args *a, const double *d_in, double *d_out,
+                  void *d_ws, size_t ws_bytes, cudaStream_t st, const PeerInfo *peer);
+int ps_peer_layout(const pspace_ctx *ctx, const pspace_project_args *a, int world, long long *recv_elems);
+int ps_peer_reduce_gather(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_recv, double *const *peer_out,
+                          int world, int rank, cudaStream_t st);

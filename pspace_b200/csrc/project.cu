@@ -61,6 +61,10 @@ struct ProjParams {
   const int *tile_list;        // fast path with a mask: ids of the tiles that contain at least one kept pair ...
   const int *tile_count;       // ... and how many there are (device scalars: no host round trip)
   int symmetric;               // matrix mode, square window: compute pairs j >= i only and mirror the block to (j,i)
+  // EPI_PEER: receive buffers of all ranks (peer-mapped), layout [src rank][owned pair tile][BM rows][ncols_pad]
+  double *peer_recv[PSPACE_MAX_PEERS];
+  int peer_world, peer_rank, peer_lp;      // ranks, my rank, pair tiles owned per rank (owner = pair tile / peer_lp)
+  long long peer_ncols_pad;                // tiles_n * BN
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gptr, int src_bytes) {
@@ -465,9 +469,15 @@ __global__ void __launch_bounds__(256) k_psi_panel(const __grid_constant__ Panel
   }
 }
 
-// MASKED = a basis-pair filter is present (tile list + masked epilogue); a separate instantiation so that the dense
-// kernel's code generation is not perturbed by the filter logic (it cost 1.3 % when it was a run-time branch).
-template <class TL, bool MASKED>
+// EPI selects the epilogue / tile enumeration; separate instantiations so that the dense kernel's code generation is
+// not perturbed by the other variants (a run-time mask branch in the epilogue cost 1.3 %):
+//   EPI_DENSE  every tile of the window, result stored to C
+//   EPI_MASKED a basis-pair filter or the i<->j symmetry: device tile list + masked / mirrored stores
+//   EPI_PEER   multi-GPU fused reduce-scatter: the finished partial tile is PUSHED over NVLink into the receive slot of
+//              the rank that owns the tile (peer-mapped symmetric memory), overlapping the exchange with the math of
+//              the following tiles; k_peer_reduce_gather finishes the collective
+enum { EPI_DENSE = 0, EPI_MASKED = 1, EPI_PEER = 2 };
+template <class TL, int EPI>
 __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__ ProjParams p,
                                                          const __grid_constant__ CUtensorMap tmapB,
                                                          const __grid_constant__ CUtensorMap tmapI,
@@ -494,6 +504,7 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
   // the pieces of each remainder tile in CTA order (deterministic).  No wave-quantisation tail.
   const int G = gridDim.x, gcta = blockIdx.x;
   const int nchunk = (int)((p.q1 - p.q0 + KQ - 1) / KQ);
+  constexpr bool MASKED = EPI == EPI_MASKED;
   const int ntiles = MASKED ? *p.tile_count : p.tiles_i * p.tiles_j * p.tiles_n;
   const int nfull = ntiles / G;
   const long long rem_units = (long long)(ntiles - nfull * G) * nchunk;
@@ -612,7 +623,19 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
     }
 
     // ---- epilogue of this segment ----------------------------------------------------------------
-    if (slot >= 0) {
+    if (EPI == EPI_PEER && slot < 0) {
+      // whole tile finished on this rank: push the partial block into the owner's receive slot (NVLink stores)
+      const int pt = tile / p.tiles_n;
+      const int owner = min(p.peer_world - 1, pt / p.peer_lp), lp = pt - owner * p.peer_lp;
+      double *base = p.peer_recv[owner] + ((size_t)(p.peer_rank * p.peer_lp + lp) * TL::BM) * p.peer_ncols_pad + (size_t)tn * BN;
+#pragma unroll
+      for (int a = 0; a < WM; a++)
+#pragma unroll
+        for (int b = 0; b < WN; b++) {
+          const int r = (wgm * WM + a) * 8 + g, cc = wgn * WN * 8 + b * 8 + 2 * kl;
+          *reinterpret_cast<double2 *>(base + (size_t)r * p.peer_ncols_pad + cc) = make_double2(acc[a][b][0], acc[a][b][1]);
+        }
+    } else if (slot >= 0) {
       // partial tile -> stream-K workspace, dense [BM][BN], no guards (k_fixup applies them)
       double *wsp = p.sk_ws + ((size_t)gcta * 2 + slot) * (TL::BM * BN);
 #pragma unroll
@@ -734,6 +757,12 @@ __global__ void __launch_bounds__(256) k_fixup(const __grid_constant__ ProjParam
       const int slot = (a0 / nchunk == rt) ? 0 : 1;
       sum += p.sk_ws[((size_t)g * 2 + slot) * ((size_t)BM * BN) + e];
     }
+    if (p.peer_world > 0) {          // fused multi-GPU mode: the summed partial tile goes to its owner's receive slot
+      const int pt = tile / p.tiles_n;
+      const int owner = min(p.peer_world - 1, pt / p.peer_lp), lp = pt - owner * p.peer_lp;
+      p.peer_recv[owner][((size_t)(p.peer_rank * p.peer_lp + lp) * BM + r) * p.peer_ncols_pad + (size_t)tn * BN + cc] = sum;
+      continue;
+    }
     const int col = col0 + cc;
     if (col >= p.ncols_d) continue;
     long long rowoff, mirroff = -1;
@@ -755,6 +784,43 @@ __global__ void __launch_bounds__(256) k_fixup(const __grid_constant__ ProjParam
     double *dst = p.out + rowoff + col;
     *dst = p.accumulate ? *dst + sum : sum;
     if (mirroff >= 0) { double *md = p.out + mirroff + col; *md = p.accumulate ? *md + sum : sum; }
+  }
+}
+
+// Second half of the fused collective.  Every rank owns peer_lp consecutive pair tiles; after all ranks' pushes have
+// landed (cross-rank barrier), the owner adds the `world` partial blocks of each owned element in rank order
+// (deterministic) and stores the total into the output of EVERY rank (peer-mapped): reduce-scatter + all-gather.
+struct PeerGatherParams {
+  const double *recv;                     // my receive buffer [world][peer_lp][BM][ncols_pad]
+  double *peer_out[PSPACE_MAX_PEERS];     // the C windows of all ranks
+  int world, rank, lp, BM, BI, tiles_j, npt;
+  long long ncols_pad, stride_i, stride_j;
+  int i0, ni, j0, nj, ncols_d, accumulate;
+};
+__global__ void __launch_bounds__(256) k_peer_reduce_gather(const __grid_constant__ PeerGatherParams p) {
+  const int lp = blockIdx.x, pt = p.rank * p.lp + lp;
+  if (pt >= p.npt) return;
+  const int ti = pt / p.tiles_j, tj = pt % p.tiles_j;
+  const size_t slot_elems = (size_t)p.lp * p.BM * p.ncols_pad;
+  const int half = (int)(p.ncols_pad / 2);                 // ncols_pad is even (BN is a multiple of 8)
+  for (int e = threadIdx.x; e < p.BM * half; e += blockDim.x) {
+    const int r = e / half, c2 = (e % half) * 2;
+    const int i = p.i0 + ti * p.BI + r / 8, j = p.j0 + tj * 8 + (r & 7);
+    if (i >= p.i0 + p.ni || j >= p.j0 + p.nj || c2 >= p.ncols_d) continue;
+    const size_t off = ((size_t)lp * p.BM + r) * p.ncols_pad + c2;
+    double2 s = *reinterpret_cast<const double2 *>(p.recv + off);
+    for (int w = 1; w < p.world; w++) {
+      const double2 v = *reinterpret_cast<const double2 *>(p.recv + w * slot_elems + off);
+      s.x += v.x; s.y += v.y;
+    }
+    const long long o = (long long)(i - p.i0) * p.stride_i + (long long)(j - p.j0) * p.stride_j + c2;
+    const bool two = c2 + 1 < p.ncols_d;
+    for (int w = 0; w < p.world; w++) {
+      double *dst = p.peer_out[w] + o;
+      if (p.accumulate) { dst[0] += s.x; if (two) dst[1] += s.y; }
+      else if (two && ((reinterpret_cast<size_t>(dst) & 15) == 0)) *reinterpret_cast<double2 *>(dst) = s;
+      else { dst[0] = s.x; if (two) dst[1] = s.y; }
+    }
   }
 }
 
@@ -896,8 +962,11 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
     } else tmI = tmJ;
     static bool attr_ws = false;
     if (!attr_ws) {
-      PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      if (MAT) PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, MAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      if (MAT) {
+        PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, MAT ? EPI_MASKED : EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, MAT ? EPI_PEER : EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      }
       attr_ws = true;
     }
     p.out = d_out;
@@ -917,8 +986,9 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
       if (!a->accumulate && !p.symmetric) PS_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * pl.out_elems, st));
       fix_blocks = pl.sk_grid - 1;     // remainder tile count is only known on the device
     }
-    if (MAT && (p.mask || p.symmetric)) k_project_ws<TL, MAT><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);   // MAT == true here: the masked instantiation
-    else k_project_ws<TL, false><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
+    if (MAT && p.peer_world > 0) k_project_ws<TL, MAT ? EPI_PEER : EPI_DENSE><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
+    else if (MAT && (p.mask || p.symmetric)) k_project_ws<TL, MAT ? EPI_MASKED : EPI_DENSE><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
+    else k_project_ws<TL, EPI_DENSE><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
     PS_LAUNCH_CHECK(c);
     if (fix_blocks > 0) {
       k_fixup<<<fix_blocks, 256, 0, st>>>(p, pl.sk_grid, TL::BM, TL::BN, TL::BI, TL::NJ, MAT ? 1 : 0);
@@ -1086,12 +1156,55 @@ size_t ps_project_workspace(const pspace_ctx *c, int is_matrix, const pspace_pro
 
 int ps_project(const pspace_ctx *c, int is_matrix, const pspace_project_args *a, const double *d_in, double *d_out,
                void *d_ws, size_t ws_bytes, cudaStream_t st) {
+  return ps_project_ex(c, is_matrix, a, d_in, d_out, d_ws, ws_bytes, st, nullptr);
+}
+
+// geometry of the fused multi-GPU exchange: doubles each rank must provide as its receive buffer
+int ps_peer_layout(const pspace_ctx *c, const pspace_project_args *a, int world, long long *recv_elems) {
+  Plan pl;
+  int rc = make_plan(c, 1, a, pl);
+  if (rc) return rc;
+  if (world < 1 || world > PSPACE_MAX_PEERS) return ps_fail(PSPACE_EINVAL, "world %d outside 1..%d", world, PSPACE_MAX_PEERS);
+  const Variant &v = MAT_VARIANTS[pl.variant_idx];
+  const long long npt = (long long)pl.tiles_i * pl.tiles_j, lp = (npt + world - 1) / world;
+  *recv_elems = (long long)world * lp * v.BM * ((long long)pl.tiles_n * v.BN);
+  return PSPACE_OK;
+}
+
+int ps_peer_reduce_gather(const pspace_ctx *c, const pspace_project_args *a, const double *d_recv, double *const *peer_out,
+                          int world, int rank, cudaStream_t st) {
+  Plan pl;
+  int rc = make_plan(c, 1, a, pl);
+  if (rc) return rc;
+  const Variant &v = MAT_VARIANTS[pl.variant_idx];
+  PeerGatherParams g;
+  g.recv = d_recv;
+  for (int w = 0; w < PSPACE_MAX_PEERS; w++) g.peer_out[w] = w < world ? peer_out[w] : nullptr;
+  g.world = world; g.rank = rank;
+  g.npt = pl.tiles_i * pl.tiles_j;
+  g.lp = (g.npt + world - 1) / world;
+  g.BM = v.BM; g.BI = v.BI; g.tiles_j = pl.tiles_j;
+  g.ncols_pad = (long long)pl.tiles_n * v.BN;
+  const int ncols_d = a->ncols * c->width;
+  g.i0 = a->k0; g.ni = a->k1 - a->k0; g.j0 = a->j0; g.nj = a->j1 - a->j0;
+  g.stride_j = ncols_d; g.stride_i = (long long)g.nj * ncols_d;
+  g.ncols_d = ncols_d; g.accumulate = a->accumulate;
+  if (g.lp > 0) {
+    k_peer_reduce_gather<<<g.lp, 256, 0, st>>>(g);
+    PS_LAUNCH_CHECK(c);
+  }
+  return PSPACE_OK;
+}
+
+int ps_project_ex(const pspace_ctx *c, int is_matrix, const pspace_project_args *a, const double *d_in, double *d_out,
+                  void *d_ws, size_t ws_bytes, cudaStream_t st, const PeerInfo *peer) {
   Plan pl;
   int rc = make_plan(c, is_matrix, a, pl);
   if (rc) return rc;
   pspace_ctx *mc = const_cast<pspace_ctx *>(c);
   const int ncols_d = a->ncols * c->width;
   if (pl.out_elems == 0) return PSPACE_OK;
+  if (pl.nchunk == 0 && peer) return ps_fail(PSPACE_EINVAL, "fused peer projection: this rank's quadrature shard is empty");
   if (pl.nchunk == 0) {   // empty q range: the projection is zero
     if (!a->accumulate) PS_CUDA(cudaMemsetAsync(d_out, 0, pl.out_elems * sizeof(double), st));
     return PSPACE_OK;
@@ -1120,6 +1233,19 @@ int ps_project(const pspace_ctx *c, int is_matrix, const pspace_project_args *a,
   p.out = d_out; p.slice_stride = 0; p.accumulate = a->accumulate; p.sk_ws = nullptr;
   p.mask = is_matrix ? a->d_pair_mask : nullptr; p.mask_ld = c->N; p.tile_list = nullptr; p.tile_count = nullptr;
   p.symmetric = 0;
+  p.peer_world = 0; p.peer_rank = 0; p.peer_lp = 1; p.peer_ncols_pad = 0;
+  for (int w = 0; w < PSPACE_MAX_PEERS; w++) p.peer_recv[w] = nullptr;
+  if (peer) {
+    if (!is_matrix || a->d_pair_mask || a->symmetric || a->accumulate)
+      return ps_fail(PSPACE_EINVAL, "fused peer projection: matrix mode without mask / symmetric / accumulate");
+    if (!(p.vec16 && !c->force_generic)) return ps_fail(PSPACE_EINVAL, "fused peer projection needs a TMA-addressable operand (even column count, 16-byte aligned)");
+    const Variant &pv = MAT_VARIANTS[pl.variant_idx];
+    const int npt = pl.tiles_i * pl.tiles_j;
+    p.peer_world = peer->world; p.peer_rank = peer->rank;
+    p.peer_lp = (npt + peer->world - 1) / peer->world;
+    p.peer_ncols_pad = (long long)pl.tiles_n * pv.BN;
+    for (int w = 0; w < peer->world; w++) p.peer_recv[w] = peer->recv[w];
+  }
   if (is_matrix && a->symmetric) {
     if (a->k0 != a->j0 || a->k1 != a->j1) return ps_fail(PSPACE_EINVAL, "symmetric projection needs a square window (i range == j range)");
     if (a->d_pair_mask) return ps_fail(PSPACE_EINVAL, "symmetric and d_pair_mask cannot be combined");

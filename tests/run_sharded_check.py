@@ -45,6 +45,10 @@ def main():
         Ch = torch.empty((40, o.N, m2), dtype=C.dtype).pin_memory()
         sp.projectMatrixHost(torch.from_numpy(np.ascontiguousarray(J[sp.q0:sp.q1])).pin_memory(), Ch, 0, 40, 0, o.N)
         F = sp.projectVector(Jl)
+        from pspace_b200.fused import FusedShardedProjector
+        fp = FusedShardedProjector(c, 0, 40, 0, o.N, ncols=m2)
+        Cf = fp.projectMatrix(Jl).clone()
+        Cf2 = fp.projectMatrix(Jl).clone()                                       # slots reused: second call must agree bitwise
         ref = o.project_matrix(J, 0, 40, 0, o.N, nthreads=8)
         refF = o.project_vector(J)
         den = np.max(np.abs(ref))
@@ -52,14 +56,17 @@ def main():
         e_rs = float(np.max(np.abs(rows.cpu().numpy() - ref[r0:r1])) / den) if r1 > r0 else 0.0
         e_h = float(np.max(np.abs(Ch.numpy() - ref)) / den)
         e_f = float(np.max(np.abs(F.cpu().numpy() - refF)) / np.max(np.abs(refF)))
-        errs = torch.tensor([e_ar, e_rs, e_h, e_f], dtype=torch.float64, device="cuda")
+        e_fused = float(np.max(np.abs(Cf.cpu().numpy() - ref)) / den)
+        if not torch.equal(Cf, Cf2):
+            e_fused = 1.0
+        errs = torch.tensor([e_ar, e_rs, e_h, e_f, e_fused], dtype=torch.float64, device="cuda")
         dist.all_reduce(errs, op=dist.ReduceOp.MAX)
         if rank == 0:
             e = [float(x) for x in errs]
             good = max(e) < 1e-12
             ok = ok and good
             print(json.dumps({"case": name, "world": world, "N": o.N, "Q": o.Q, "m2": m2, "allreduce_err": e[0], "reduce_scatter_err": e[1],
-                              "host_input_err": e[2], "vector_err": e[3], "shards": [sp.q0, sp.q1], "pass": good}))
+                              "host_input_err": e[2], "vector_err": e[3], "fused_peer_err": e[4], "shards": [sp.q0, sp.q1], "pass": good}))
         c.close()
     dist.destroy_process_group()
     return 0 if ok else 1
