@@ -560,6 +560,13 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
     const int wgm = cw / WGN, wgn = cw % WGN;
     const int g = lane >> 2, kl = lane & 3;
     const unsigned sgn = (g & 1) ? 0u : 0x80000000u;
+    constexpr bool PAIRED = CPLX && (WN % 2) == 0;   // measured: +2.5 % on the complex build (the neighbour column comes for free), -0.7 % on the real dense kernel
+    // accumulator pair `idx` (0..WN-1) of row tile a: two values in adjacent physical columns, first column cc (relative
+    // to the warp's column span)
+    auto acc_pair = [&](const double (&ac)[WM][WN][2], int a, int idx, double &v0, double &v1, int &cc) {
+      if (PAIRED) { const int b2 = idx >> 1, e = idx & 1; v0 = ac[a][2 * b2][e]; v1 = ac[a][2 * b2 + (WN > 1 ? 1 : 0)][e]; cc = 16 * b2 + 4 * kl + 2 * e; }
+      else { v0 = ac[a][idx][0]; v1 = ac[a][idx][1]; cc = 8 * idx + 2 * kl; }
+    };
     int it = 0;
     for (int sidx = 0; sidx < nseg; sidx++) {
     int tile, c0, c1, slot;
@@ -578,6 +585,7 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
       mbar_wait(&full[s], n & 1u);
       const unsigned char *st = stage_base + (size_t)s * LY::STAGE_BYTES;
       const double *bs = reinterpret_cast<const double *>(st) + wgn * WN * 8 + g;
+      const double *bs2 = reinterpret_cast<const double *>(st) + wgn * WN * 8 + 2 * g;
       const double *pj = reinterpret_cast<const double *>(st + LY::PJ_OFF);
       const double *pi = reinterpret_cast<const double *>(st + LY::PI_OFF);
 #pragma unroll
@@ -605,10 +613,22 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
           }
         }
         double bfr[WN], bsw[WN];
+        if (PAIRED) {
+          // one 16-byte load = physical columns (2g, 2g+1) of a 16-column group: the even one feeds column tile 2*b2, the
+          // odd one tile 2*b2+1 (column tiles are just a labelling of the columns; the epilogue undoes it).  Halves the
+          // B-fragment loads; in the complex build the neighbour column is the other half of the same load.
 #pragma unroll
-        for (int b = 0; b < WN; b++) {
-          bfr[b] = bs[k * LDB + b * 8];
-          if (CPLX) bsw[b] = flip_sign(bs[k * LDB + b * 8 + ((g & 1) ? -1 : 1)], sgn);
+          for (int b2 = 0; b2 < WN / 2; b2++) {
+            const double2 v = *reinterpret_cast<const double2 *>(bs2 + k * LDB + 16 * b2);
+            bfr[2 * b2] = v.x; bfr[2 * b2 + 1] = v.y;
+            if (CPLX) { bsw[2 * b2] = flip_sign(v.y, 0x80000000u); bsw[2 * b2 + 1] = v.x; }
+          }
+        } else {
+#pragma unroll
+          for (int b = 0; b < WN; b++) {
+            bfr[b] = bs[k * LDB + b * 8];
+            if (CPLX) bsw[b] = flip_sign(bs[k * LDB + b * 8 + ((g & 1) ? -1 : 1)], sgn);
+          }
         }
 #pragma unroll
         for (int a = 0; a < WM; a++)
@@ -632,8 +652,10 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
       for (int a = 0; a < WM; a++)
 #pragma unroll
         for (int b = 0; b < WN; b++) {
-          const int r = (wgm * WM + a) * 8 + g, cc = wgn * WN * 8 + b * 8 + 2 * kl;
-          *reinterpret_cast<double2 *>(base + (size_t)r * p.peer_ncols_pad + cc) = make_double2(acc[a][b][0], acc[a][b][1]);
+          double v0, v1; int cw_;
+          acc_pair(acc, a, b, v0, v1, cw_);
+          const int r = (wgm * WM + a) * 8 + g, cc = wgn * WN * 8 + cw_;
+          *reinterpret_cast<double2 *>(base + (size_t)r * p.peer_ncols_pad + cc) = make_double2(v0, v1);
         }
     } else if (slot >= 0) {
       // partial tile -> stream-K workspace, dense [BM][BN], no guards (k_fixup applies them)
@@ -642,8 +664,10 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
       for (int a = 0; a < WM; a++)
 #pragma unroll
         for (int b = 0; b < WN; b++) {
-          const int r = (wgm * WM + a) * 8 + g, cc = wgn * WN * 8 + b * 8 + 2 * kl;
-          *reinterpret_cast<double2 *>(wsp + (size_t)r * BN + cc) = make_double2(acc[a][b][0], acc[a][b][1]);
+          double v0, v1; int cw_;
+          acc_pair(acc, a, b, v0, v1, cw_);
+          const int r = (wgm * WM + a) * 8 + g, cc = wgn * WN * 8 + cw_;
+          *reinterpret_cast<double2 *>(wsp + (size_t)r * BN + cc) = make_double2(v0, v1);
         }
     } else {
 #pragma unroll
@@ -667,9 +691,11 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
       if (MASKED && !keep && (p.accumulate || p.symmetric)) continue;   // filtered pair: nothing to add / written by its mirror
 #pragma unroll
       for (int b = 0; b < WN; b++) {
-        const int col = col0 + wgn * WN * 8 + b * 8 + 2 * kl;
+        double a0, a1; int cw_;
+        acc_pair(acc, a, b, a0, a1, cw_);
+        const int col = col0 + wgn * WN * 8 + cw_;
         double *dst = p.out + rowoff + col;
-        double v0 = (!MASKED || keep) ? acc[a][b][0] : 0.0, v1 = (!MASKED || keep) ? acc[a][b][1] : 0.0;
+        double v0 = (!MASKED || keep) ? a0 : 0.0, v1 = (!MASKED || keep) ? a1 : 0.0;
         if (col + 1 < p.ncols_d && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
           if (p.accumulate) { const double2 o = *reinterpret_cast<double2 *>(dst); v0 += o.x; v1 += o.y; }
           *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
@@ -679,7 +705,7 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
         }
         if (MASKED && mirroff >= 0) {
           double *md = p.out + mirroff + col;
-          double w0 = acc[a][b][0], w1 = acc[a][b][1];
+          double w0 = a0, w1 = a1;
           if (col < p.ncols_d) md[0] = p.accumulate ? md[0] + w0 : w0;
           if (col + 1 < p.ncols_d) md[1] = p.accumulate ? md[1] + w1 : w1;
         }
