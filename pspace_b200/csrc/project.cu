@@ -61,6 +61,7 @@ struct ProjParams {
   const int *tile_list;        // fast path with a mask: ids of the tiles that contain at least one kept pair ...
   const int *tile_count;       // ... and how many there are (device scalars: no host round trip)
   int symmetric;               // matrix mode, square window: compute pairs j >= i only and mirror the block to (j,i)
+  int zero;                    // always 0, but only known at run time (see the stage release in k_project_ws)
   // EPI_PEER: receive buffers of all ranks (peer-mapped), layout [src rank][owned pair tile][BM rows][ncols_pad]
   double *peer_recv[PSPACE_MAX_PEERS];
   int peer_world, peer_rank, peer_lp;      // ranks, my rank, pair tiles owned per rank (owner = pair tile / peer_lp)
@@ -643,6 +644,14 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
     }
 
     // ---- epilogue of this segment ----------------------------------------------------------------
+    // All 8 consumer warps meet here before any of them starts storing.  Reason: a stage is refilled by TMA once all
+    // warps have arrived on empty[s], and ptxas issues that arrive right after the last fragment LDS is *issued*.  If a
+    // warp that is still in the tile's last chunks had its LDS queued behind the epilogue stores of warps that are
+    // already done (seen with the slow remote NVLink stores of EPI_PEER: 1e-10 glitches in that warp's last column
+    // tile), the arrive and the refill could overtake the load.  With this barrier no store is in flight while any warp
+    // of the CTA still reads fragments of the tile; after it, the last-arriving warp of the next tile's first chunks
+    // has completed its own stores (EPI_PEER: __threadfence_system below), so the load/store queue is empty again.
+    asm volatile("bar.sync 1, %0;\n" ::"n"(NT_WS - NPROD) : "memory");
     if (EPI == EPI_PEER && slot < 0) {
       // whole tile finished on this rank: push the partial block into the owner's receive slot (NVLink stores)
       const int pt = tile / p.tiles_n;
@@ -657,6 +666,7 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
           const int r = (wgm * WM + a) * 8 + g, cc = wgn * WN * 8 + cw_;
           *reinterpret_cast<double2 *>(base + (size_t)r * p.peer_ncols_pad + cc) = make_double2(v0, v1);
         }
+      __threadfence_system();      // peer stores must have landed at the owner before this kernel is seen as complete
     } else if (slot >= 0) {
       // partial tile -> stream-K workspace, dense [BM][BN], no guards (k_fixup applies them)
       double *wsp = p.sk_ws + ((size_t)gcta * 2 + slot) * (TL::BM * BN);
@@ -787,6 +797,7 @@ __global__ void __launch_bounds__(256) k_fixup(const __grid_constant__ ProjParam
       const int pt = tile / p.tiles_n;
       const int owner = min(p.peer_world - 1, pt / p.peer_lp), lp = pt - owner * p.peer_lp;
       p.peer_recv[owner][((size_t)(p.peer_rank * p.peer_lp + lp) * BM + r) * p.peer_ncols_pad + (size_t)tn * BN + cc] = sum;
+      __threadfence_system();
       continue;
     }
     const int col = col0 + cc;
@@ -848,6 +859,7 @@ __global__ void __launch_bounds__(256) k_peer_reduce_gather(const __grid_constan
       else { dst[0] = s.x; if (two) dst[1] = s.y; }
     }
   }
+  __threadfence_system();
 }
 
 // TMA descriptors (fp64, no swizzle, zero fill out of bounds).  dims/box innermost first.
@@ -1259,6 +1271,7 @@ int ps_project_ex(const pspace_ctx *c, int is_matrix, const pspace_project_args 
   p.out = d_out; p.slice_stride = 0; p.accumulate = a->accumulate; p.sk_ws = nullptr;
   p.mask = is_matrix ? a->d_pair_mask : nullptr; p.mask_ld = c->N; p.tile_list = nullptr; p.tile_count = nullptr;
   p.symmetric = 0;
+  p.zero = 0;
   p.peer_world = 0; p.peer_rank = 0; p.peer_lp = 1; p.peer_ncols_pad = 0;
   for (int w = 0; w < PSPACE_MAX_PEERS; w++) p.peer_recv[w] = nullptr;
   if (peer) {
