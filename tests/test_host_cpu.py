@@ -154,3 +154,20 @@ def test_bench_reference_arm_prints_contract_line():
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
                         text=True, timeout=60, env=env)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_header_is_plain_c_and_matches_the_ctypes_binding(tmp_path):
+    """The boundary is a C ABI: include/pspace_cuda.h must compile as C99, and the struct the Python binding passes
+    (ProjectArgs) must have the size and field offsets the C compiler gives pspace_project_args."""
+    import ctypes
+    from pspace_b200.cabi import ProjectArgs
+    src = tmp_path / "abi.c"
+    fields = [f[0] for f in ProjectArgs._fields_]
+    body = "".join(f'printf("%zu\\n", offsetof(pspace_project_args, {f}));' for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pspace_cuda.h"\n'
+                   'int main(void){ printf("%zu\\n", sizeof(pspace_project_args)); ' + body + ' return 0; }\n')
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    assert out[0] == ctypes.sizeof(ProjectArgs)
+    assert out[1:] == [getattr(ProjectArgs, f).offset for f in fields]
