@@ -171,3 +171,18 @@ def test_header_is_plain_c_and_matches_the_ctypes_binding(tmp_path):
     out = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     assert out[0] == ctypes.sizeof(ProjectArgs)
     assert out[1:] == [getattr(ProjectArgs, f).offset for f in fields]
+
+
+def test_dense_dmma_loop_keeps_the_fast_ptxas_schedule():
+    """Static guard (no GPU): ptxas emits one of two schedules for the DMMA loop of the dense 128x96 real tile depending on
+    unrelated code in the kernel; the slower one (>= 3170 static stall cycles per chunk and warp) measures 1.2 % slower on
+    the B200.  tools/sass_loop_stats.py decodes the control words of the built library."""
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "sass_loop_stats.py"),
+                                   "Li2ELi12ELi8ELi1ELb0ELi0ELi4ELi1EEELi0"], text=True)
+    m = re.search(r"DMMA\s+(\d+)\s+static stall cycles/chunk\s+(\d+)", out)
+    assert m, out
+    assert int(m.group(1)) == 192                      # 8 k-steps x 2 row tiles x 12 column tiles
+    assert int(m.group(2)) <= 3160, out                # 192 x 16 = 3072 is the floor; 3152 today
