@@ -402,9 +402,13 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, 
 
 template <class TL> struct WsLayout {
   static constexpr int W = TL::W;
-  static constexpr int B_BYTES = KQ * TL::LDB * 8;
-  static constexpr int PJ_BYTES = W * KQ * TL::PJP * 8;
-  static constexpr int PI_BYTES = (TL::MODE == MODE_MATRIX) ? W * KQ * TL::BIP * 8 : 0;
+  // quadrature points per pipeline stage of the fast kernel: 64 for real scalars (16 k-steps = 384 DMMAs per warp between
+  // two chunk boundaries, halving the per-chunk overhead of barrier wait + first fragment loads), 32 for complex (already
+  // 384 DMMAs per chunk)
+  static constexpr int KQW = TL::CPLX ? 32 : 64;
+  static constexpr int B_BYTES = KQW * TL::LDB * 8;
+  static constexpr int PJ_BYTES = W * KQW * TL::PJP * 8;
+  static constexpr int PI_BYTES = (TL::MODE == MODE_MATRIX) ? W * KQW * TL::BIP * 8 : 0;
   // every TMA destination must be 128-byte aligned
   static constexpr int PJ_OFF = ((B_BYTES + 127) / 128) * 128;
   static constexpr int PI_OFF = ((PJ_OFF + PJ_BYTES + 127) / 128) * 128;
@@ -488,6 +492,7 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
   constexpr int LDB = TL::LDB, BIP = TL::BIP, PJP = TL::PJP, STAGES = LY::STAGES;
   constexpr bool CPLX = TL::CPLX;
   constexpr bool MAT = TL::MODE == MODE_MATRIX;
+  constexpr int KQ = LY::KQW;          // shadows the generic kernel's chunk size
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char *stage_base = smem_raw;
@@ -767,8 +772,8 @@ __global__ void __launch_bounds__(256) k_tile_list(const unsigned char *mask, in
 // Adds the stream-K pieces of each remainder tile in CTA order and stores the tile (guards, accumulate).
 // One block per remainder tile.  Geometry arguments restate k_project_ws's decomposition.
 __global__ void __launch_bounds__(256) k_fixup(const __grid_constant__ ProjParams p, int G, int BM, int BN, int BI, int NJ,
-                                               int matrix) {
-  const int nchunk = (int)((p.q1 - p.q0 + KQ - 1) / KQ);
+                                               int matrix, int kq) {
+  const int nchunk = (int)((p.q1 - p.q0 + kq - 1) / kq);
   const int ntiles = p.tile_list ? *p.tile_count : p.tiles_i * p.tiles_j * p.tiles_n;
   const int nfull = ntiles / G;
   const long long rem_units = (long long)(ntiles - nfull * G) * nchunk;
@@ -983,19 +988,19 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
     CUtensorMap tmB, tmI, tmJ;
     {
       unsigned long long dims[2] = {(unsigned long long)p.ncols_d, nq}, str[1] = {(unsigned long long)p.ld_in * 8};
-      unsigned box[2] = {(unsigned)TL::LDB, (unsigned)KQ};
+      unsigned box[2] = {(unsigned)TL::LDB, (unsigned)LY::KQW};
       if ((rc = make_tmap(&tmB, p.in, 2, dims, str, box))) return rc;
     }
     {
       unsigned long long dims[3] = {(unsigned long long)nj_pad, nq, (unsigned long long)TL::W};
       unsigned long long str[2] = {(unsigned long long)nj_pad * 8, (unsigned long long)nj_pad * 8 * nq};
-      unsigned box[3] = {(unsigned)TL::PJP, (unsigned)KQ, (unsigned)TL::W};
+      unsigned box[3] = {(unsigned)TL::PJP, (unsigned)LY::KQW, (unsigned)TL::W};
       if ((rc = make_tmap(&tmJ, d_pj, 3, dims, str, box))) return rc;
     }
     if (MAT) {
       unsigned long long dims[3] = {(unsigned long long)ni_pad, nq, (unsigned long long)TL::W};
       unsigned long long str[2] = {(unsigned long long)ni_pad * 8, (unsigned long long)ni_pad * 8 * nq};
-      unsigned box[3] = {(unsigned)TL::BIP, (unsigned)KQ, (unsigned)TL::W};
+      unsigned box[3] = {(unsigned)TL::BIP, (unsigned)LY::KQW, (unsigned)TL::W};
       if ((rc = make_tmap(&tmI, d_pi, 3, dims, str, box))) return rc;
     } else tmI = tmJ;
     static bool attr_ws = false;
@@ -1029,7 +1034,7 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
     else k_project_ws<TL, EPI_DENSE><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
     PS_LAUNCH_CHECK(c);
     if (fix_blocks > 0) {
-      k_fixup<<<fix_blocks, 256, 0, st>>>(p, pl.sk_grid, TL::BM, TL::BN, TL::BI, TL::NJ, MAT ? 1 : 0);
+      k_fixup<<<fix_blocks, 256, 0, st>>>(p, pl.sk_grid, TL::BM, TL::BN, TL::BI, TL::NJ, MAT ? 1 : 0, LY::KQW);
       PS_LAUNCH_CHECK(c);
     }
     if (d_list) PS_CUDA(cudaFreeAsync(d_list, st));

@@ -175,7 +175,7 @@ def test_header_is_plain_c_and_matches_the_ctypes_binding(tmp_path):
 
 def test_dense_dmma_loop_keeps_the_fast_ptxas_schedule():
     """Static guard (no GPU): ptxas emits one of two schedules for the DMMA loop of the dense 128x96 real tile depending on
-    unrelated code in the kernel; the slower one (>= 3170 static stall cycles per chunk and warp) measures 1.2 % slower on
+    unrelated code in the kernel; the slower one (about 40 more static stall cycles per 32 points and warp) measures 1.2 % slower on
     the B200.  tools/sass_loop_stats.py decodes the control words of the built library."""
     import shutil
     if not shutil.which("cuobjdump"):
@@ -184,5 +184,5 @@ def test_dense_dmma_loop_keeps_the_fast_ptxas_schedule():
                                    "Li2ELi12ELi8ELi1ELb0ELi0ELi4ELi1EEELi0"], text=True)
     m = re.search(r"DMMA\s+(\d+)\s+static stall cycles/chunk\s+(\d+)", out)
     assert m, out
-    assert int(m.group(1)) == 192                      # 8 k-steps x 2 row tiles x 12 column tiles
-    assert int(m.group(2)) <= 3160, out                # 192 x 16 = 3072 is the floor; 3152 today
+    assert int(m.group(1)) == 384                      # 16 k-steps (64-point stage) x 2 row tiles x 12 column tiles
+    assert int(m.group(2)) <= 6290, out                # 384 x 16 = 6144 is the floor; 6256 today (the slower schedule: >= 6300)
