@@ -175,8 +175,20 @@ int ps_expand(const pspace_ctx *c, int k0, int k1, long long q0, long long q1, i
   p.accumulate = accumulate;
   p.vecV = (ncols_d % 2 == 0 && (reinterpret_cast<size_t>(d_V) % 16) == 0) ? 1 : 0;
   const bool z = c->is_complex;
-  if (ncols_d > 32) rc = z ? launch_expand<8, true>(c, p, st) : launch_expand<8, false>(c, p, st);
-  else if (ncols_d > 8) rc = z ? launch_expand<4, true>(c, p, st) : launch_expand<4, false>(c, p, st);
-  else rc = z ? launch_expand<1, true>(c, p, st) : launch_expand<1, false>(c, p, st);
+  // warp tile width WN*8 columns: fewest column tiles first (every column tile streams the panel again), then the
+  // fewest padded columns
+  static const int cand[] = {8, 6, 4, 3, 2, 1};
+  const int min_tiles = (ncols_d + 63) / 64;
+  int wn = 8;
+  for (int k = 0; k < 6; k++)
+    if ((ncols_d + cand[k] * 8 - 1) / (cand[k] * 8) == min_tiles) wn = cand[k];
+  switch (wn) {
+    case 8: rc = z ? launch_expand<8, true>(c, p, st) : launch_expand<8, false>(c, p, st); break;
+    case 6: rc = z ? launch_expand<6, true>(c, p, st) : launch_expand<6, false>(c, p, st); break;
+    case 4: rc = z ? launch_expand<4, true>(c, p, st) : launch_expand<4, false>(c, p, st); break;
+    case 3: rc = z ? launch_expand<3, true>(c, p, st) : launch_expand<3, false>(c, p, st); break;
+    case 2: rc = z ? launch_expand<2, true>(c, p, st) : launch_expand<2, false>(c, p, st); break;
+    default: rc = z ? launch_expand<1, true>(c, p, st) : launch_expand<1, false>(c, p, st); break;
+  }
   return rc;
 }

@@ -5,7 +5,7 @@
 // examples/ouu/twobartruss/stochastic_two_bar_truss.py:99-114).  psi_0 is the degree-0 basis function (the first
 // row of the graded degree table), which the orthonormal families evaluate to exactly 1.
 // HBM bound: f is read once (8*ncols bytes per point).  Deterministic: fixed q-slices per block, fixed-order
-// shared-memory reduction, slices added in order by k_moments_final.
+// shared-memory reduction, slices added in a fixed order by k_moments_final (a warp per column).
 #include "ctx.h"
 #include <algorithm>
 
@@ -77,16 +77,29 @@ __global__ void __launch_bounds__(MT) k_moments_partial(const double *f, const d
   }
 }
 
+// one warp per column: lane l adds the slices l, l+32, ... in order, then a fixed xor-shuffle tree over the lanes
+// (deterministic; the partials of a column are read by 32 lanes at once instead of one thread walking every slice)
 template <bool CPLX>
-__global__ void k_moments_final(const double *part, int slices, int ncols, double *mean, double *second, double *var) {
+__global__ void __launch_bounds__(128) k_moments_final(const double *part, int slices, int ncols, double *mean,
+                                                        double *second, double *var) {
   constexpr int WD = CPLX ? 2 : 1;
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= ncols) return;
+  const int lane = threadIdx.x & 31;
+  const int col = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (col >= ncols) return;                    // warp-uniform
   double m[2] = {0, 0}, s[2] = {0, 0};
-  for (int b = 0; b < slices; b++) {
+  for (int b = lane; b < slices; b += 32) {
     const double *src = part + (size_t)b * 2 * ncols * WD;
+#pragma unroll
     for (int k = 0; k < WD; k++) { m[k] += src[col * WD + k]; s[k] += src[(size_t)ncols * WD + col * WD + k]; }
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int k = 0; k < WD; k++) {
+      m[k] += __shfl_xor_sync(0xffffffffu, m[k], off);
+      s[k] += __shfl_xor_sync(0xffffffffu, s[k], off);
+    }
+  if (lane != 0) return;
   for (int k = 0; k < WD; k++) {
     if (mean) mean[col * WD + k] = m[k];
     if (second) second[col * WD + k] = s[k];
@@ -118,8 +131,8 @@ extern "C" int pspace_cuda_moments(const pspace_ctx *c, long long q0, long long 
   if (c->is_complex) k_moments_partial<true><<<grid, MT, 0, st>>>(d_f, c->d_W, q0, nq, ncols, ct, rows_per_slice, part);
   else k_moments_partial<false><<<grid, MT, 0, st>>>(d_f, c->d_W, q0, nq, ncols, ct, rows_per_slice, part);
   PS_LAUNCH_CHECK(c);
-  if (c->is_complex) k_moments_final<true><<<(ncols + 127) / 128, 128, 0, st>>>(part, slices, ncols, d_mean, d_second, d_var);
-  else k_moments_final<false><<<(ncols + 127) / 128, 128, 0, st>>>(part, slices, ncols, d_mean, d_second, d_var);
+  if (c->is_complex) k_moments_final<true><<<(ncols + 3) / 4, 128, 0, st>>>(part, slices, ncols, d_mean, d_second, d_var);
+  else k_moments_final<false><<<(ncols + 3) / 4, 128, 0, st>>>(part, slices, ncols, d_mean, d_second, d_var);
   PS_LAUNCH_CHECK(c);
   PS_CUDA(cudaFreeAsync(part, st));
   return PSPACE_OK;

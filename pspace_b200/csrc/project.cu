@@ -429,34 +429,85 @@ struct PanelParams {
   long long q0, q1;
   int r0, nr, nr_pad;       // basis rows [r0, r0+nr), panel row pitch nr_pad (pad rows are written as zeros)
   int weighted;
+  int dsplit, tail_stride;  // variables [dsplit, nvars) are the "tail": tail_stride = prod of their rule sizes
   double *out;              // [width][q1-q0][nr_pad]
 };
 
-// one warp per quadrature point, lanes over basis rows (coalesced row-contiguous stores)
+// Basis panel P[part][q][row] = psi_row(z_q) (x w_q when weighted), product order ((1*T_0)*T_1)*... as everywhere.
+// A thread owns one basis row (its per-variable table offsets live in registers) and walks PSI_PTS consecutive
+// quadrature points of the block; the threads of a warp store 32 consecutive rows of one point (coalesced).  The
+// last variable is the fastest index of the tensor grid (QuadratureHelper.cpp:34-132), so the partial product over
+// the leading variables [0, dsplit) is the same for tail_stride consecutive points: it is kept in a register and only
+// the tail factors are multiplied per point — same left-to-right order, hence bit-identical values, with
+// (nvars - dsplit) + dsplit / tail_stride shared-memory table reads per value instead of nvars.
+constexpr int PSI_PTS = 128, PSI_MAXT = 512, PSI_TAIL = 4;
 template <bool CPLX>
-__global__ void __launch_bounds__(256) k_psi_panel(const __grid_constant__ PanelParams p) {
+__global__ void __launch_bounds__(PSI_MAXT) k_psi_panel(const __grid_constant__ PanelParams p) {
   constexpr int W = CPLX ? 2 : 1;
   extern __shared__ __align__(16) unsigned char psm[];
-  double *Ts = reinterpret_cast<double *>(psm);
-  for (int i = threadIdx.x; i < p.tsz * W; i += blockDim.x) Ts[i] = p.T[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *Ts = reinterpret_cast<double *>(psm);                        // 1-D tables, tsz scalars
+  double *Ws = Ts + ((p.tsz * W + 1) & ~1);                            // weights of the block's points
+  uint8_t *Dg = reinterpret_cast<uint8_t *>(Ws + PSI_PTS * W);         // digit rows of the block's points [PSI_PTS][DP]
   const long long nq = p.q1 - p.q0;
-  const long long r = blockIdx.x * 8LL + warp;
-  if (r >= nq) return;
-  const long long q = p.q0 + r;
-  const uint8_t *dg = p.qdig + q * p.DP;
-  int base[PSPACE_MAX_VARS];     // table offset of (variable d, digit of q), row 0
-  for (int d = 0; d < p.nvars; d++) base[d] = p.toff[d] + dg[d];
-  double wre = 1.0, wim = 0.0;
-  if (p.weighted) { wre = CPLX ? p.W[2 * q] : p.W[q]; wim = CPLX ? p.W[2 * q + 1] : 0.0; }
-  for (int row = lane; row < p.nr_pad; row += 32) {
-    double vr = 0.0, vi = 0.0;
-    if (row < p.nr) {
-      const int *dk = p.deg + (size_t)(p.r0 + row) * p.nvars;
-      vr = 1.0;
-      for (int d = 0; d < p.nvars; d++) {
-        const int o = base[d] + dk[d] * p.nq[d];
+  const long long rb0 = blockIdx.x * (long long)PSI_PTS;
+  const int npts = (int)min((long long)PSI_PTS, nq - rb0);
+  for (int i = threadIdx.x; i < p.tsz * W; i += blockDim.x) Ts[i] = p.T[i];
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.qdig + (p.q0 + rb0) * p.DP);
+    uint4 *dst = reinterpret_cast<uint4 *>(Dg);
+    for (int i = threadIdx.x; i < npts * (p.DP / 16); i += blockDim.x) dst[i] = src[i];
+    if (p.weighted)
+      for (int i = threadIdx.x; i < npts * W; i += blockDim.x) Ws[i] = p.W[(p.q0 + rb0) * W + i];
+  }
+  __syncthreads();
+  const int row = blockIdx.y * blockDim.x + threadIdx.x;
+  if (row >= p.nr_pad) return;
+  const bool live = row < p.nr;
+  int ro[PSPACE_MAX_VARS];          // table offset of (variable d, this row's degree), digit 0 — statically indexed
+  int tro[PSI_TAIL];                // the same for the tail variables
+#pragma unroll
+  for (int k = 0; k < PSI_TAIL; k++) tro[k] = 0;
+  {
+    const int *dk = p.deg + (size_t)(p.r0 + (live ? row : 0)) * p.nvars;
+#pragma unroll
+    for (int d = 0; d < PSPACE_MAX_VARS; d++) {
+      ro[d] = 0;
+      if (d < p.nvars) {
+        ro[d] = p.toff[d] + dk[d] * p.nq[d];
+#pragma unroll
+        for (int k = 0; k < PSI_TAIL; k++)
+          if (d == p.dsplit + k) tro[k] = ro[d];
+      }
+    }
+  }
+  const int ntail = p.nvars - p.dsplit;
+  int cnt = (int)((p.q0 + rb0) % p.tail_stride);
+  double pr = 1.0, pi = 0.0;
+  double *out_re = p.out + (size_t)rb0 * p.nr_pad + row;
+  double *out_im = p.out + (size_t)(nq + rb0) * p.nr_pad + row;
+  for (int t = 0; t < npts; t++) {
+    const uint8_t *dg = Dg + t * p.DP;
+    if (t == 0 || cnt == 0) {       // block-uniform: a new prefix
+      pr = 1.0; pi = 0.0;
+#pragma unroll
+      for (int d = 0; d < PSPACE_MAX_VARS; d++) {
+        if (d < p.dsplit) {
+          const int o = ro[d] + dg[d];
+          if (!CPLX) pr *= Ts[o];
+          else {
+            const double tr = Ts[2 * o], tm = Ts[2 * o + 1];
+            const double nr = pr * tr - pi * tm, ni = pr * tm + pi * tr;
+            pr = nr; pi = ni;
+          }
+        }
+      }
+    }
+    if (++cnt == p.tail_stride) cnt = 0;
+    double vr = pr, vi = pi;
+#pragma unroll
+    for (int k = 0; k < PSI_TAIL; k++) {
+      if (k < ntail) {
+        const int o = tro[k] + dg[p.dsplit + k];
         if (!CPLX) vr *= Ts[o];
         else {
           const double tr = Ts[2 * o], tm = Ts[2 * o + 1];
@@ -464,13 +515,18 @@ __global__ void __launch_bounds__(256) k_psi_panel(const __grid_constant__ Panel
           vr = nr; vi = ni;
         }
       }
-      if (p.weighted) {
-        if (!CPLX) vr *= wre;
-        else { const double nr = vr * wre - vi * wim, ni = vr * wim + vi * wre; vr = nr; vi = ni; }
+    }
+    if (p.weighted) {
+      if (!CPLX) vr *= Ws[t];
+      else {
+        const double wre = Ws[2 * t], wim = Ws[2 * t + 1];
+        const double nr = vr * wre - vi * wim, ni = vr * wim + vi * wre;
+        vr = nr; vi = ni;
       }
     }
-    p.out[r * p.nr_pad + row] = vr;
-    if (CPLX) p.out[(nq + r) * p.nr_pad + row] = vi;
+    if (!live) { vr = 0.0; vi = 0.0; }
+    out_re[(size_t)t * p.nr_pad] = vr;
+    if (CPLX) out_im[(size_t)t * p.nr_pad] = vi;
   }
 }
 
@@ -921,18 +977,32 @@ int build_panels(pspace_ctx *c, const ProjParams &p, bool matrix, double **d_pi,
   pp.T = c->d_T; pp.deg = c->d_deg; pp.qdig = c->d_qdig; pp.W = c->d_W;
   for (int d = 0; d < c->nvars; d++) { pp.toff[d] = c->toff[d]; pp.nq[d] = c->nq[d]; }
   pp.q0 = p.q0; pp.q1 = p.q1;
-  const size_t smem = (size_t)c->tsz * W * 8;
-  const unsigned nb = (unsigned)((nq + 7) / 8);
+  // tail = the trailing variables whose digits change within a block of consecutive points: pick the length that
+  // minimises table reads per value, tail + (nvars - tail) / (points sharing a prefix)
+  {
+    double best_cost = (double)c->nvars;
+    long long stride = 1;
+    pp.dsplit = c->nvars; pp.tail_stride = 1;
+    for (int t = 1; t <= PSI_TAIL && t <= c->nvars; t++) {
+      stride *= c->nq[c->nvars - t];
+      if (stride > (1 << 20)) break;
+      const double cost = t + (double)(c->nvars - t) / (double)stride;
+      if (cost < best_cost) { best_cost = cost; pp.dsplit = c->nvars - t; pp.tail_stride = (int)stride; }
+    }
+  }
+  const size_t smem = (size_t)(((c->tsz * W + 1) & ~1) + PSI_PTS * W) * 8 + (size_t)PSI_PTS * c->DP;
   for (int side = matrix ? 0 : 1; side < 2; side++) {
     pp.r0 = side ? p.j0 : p.i0; pp.nr = side ? p.nj : p.ni; pp.nr_pad = side ? *nj_pad : *ni_pad;
     pp.weighted = side; pp.out = side ? *d_pj : *d_pi;
     if (pp.nr_pad == 0) continue;
+    const int nt = std::min(PSI_MAXT, (pp.nr_pad + 31) & ~31);
+    const dim3 grid((unsigned)((nq + PSI_PTS - 1) / PSI_PTS), (unsigned)((pp.nr_pad + nt - 1) / nt));
     if (c->is_complex) {
       PS_CUDA(cudaFuncSetAttribute(k_psi_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_psi_panel<true><<<nb, 256, smem, st>>>(pp);
+      k_psi_panel<true><<<grid, nt, smem, st>>>(pp);
     } else {
       PS_CUDA(cudaFuncSetAttribute(k_psi_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_psi_panel<false><<<nb, 256, smem, st>>>(pp);
+      k_psi_panel<false><<<grid, nt, smem, st>>>(pp);
     }
     PS_LAUNCH_CHECK(c);
   }

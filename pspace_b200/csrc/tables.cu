@@ -60,7 +60,7 @@ __global__ void k_rules_tables(TabParams p, double *zp, double *yp, double *wp, 
 
 struct GridParams {
   int nvars, DP;
-  int nq[PSPACE_MAX_VARS], roff[PSPACE_MAX_VARS + 1];
+  int nq[PSPACE_MAX_VARS], roff[PSPACE_MAX_VARS + 1], toff[PSPACE_MAX_VARS + 1];
 };
 
 __device__ __forceinline__ void digits_of(const GridParams &g, long long q, int *dig) {
@@ -110,22 +110,24 @@ __global__ void k_tensor_grid(GridParams g, long long q0, long long q1, const do
 // Batched basis evaluation at quadrature points: psi[k][q] = ((1*T_0[a_0][i_0])*T_1[a_1][i_1])*...
 // (ParameterContainer.cpp:184-192 product order).  Block = 8 warps; the 1-D tables are staged in shared
 // memory; a warp owns a tile of 32 consecutive points (coalesced 256 B stores along q) and walks the
-// block's KB basis rows, whose per-variable table-row offsets are staged once per block.
+// block's KB basis rows eight at a time (eight independent product chains; their per-variable table-row
+// offsets are staged once per block, variable-major, so one chain step costs two broadcast LDS.128 + one
+// digit read for eight table lookups).
 constexpr int EB_WARPS = 8, EB_KB = 32;
 template <typename S>
-__global__ void __launch_bounds__(EB_WARPS * 32) k_eval_basis_grid(GridParams g, int tsz, const double *T,
-                                                                   const int *toff_rows /*[nvars]: toff[d]*/,
-                                                                   const int *deg, int k0, int k1, long long q0,
-                                                                   long long q1, const uint8_t *qdig, double *psi) {
+__global__ void __launch_bounds__(EB_WARPS * 32) k_eval_basis_grid(const __grid_constant__ GridParams g, int tsz,
+                                                                   const double *T, const int *deg, int k0, int k1,
+                                                                   long long q0, long long q1, const uint8_t *qdig,
+                                                                   double *psi) {
   typedef scalar_of<S> SO;
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   double *Ts = sm;                                            // tsz scalars
-  int *rowoff = reinterpret_cast<int *>(sm + (size_t)tsz * SO::width);   // [EB_KB][nvars]
+  int *rowoff = reinterpret_cast<int *>(sm + (((size_t)tsz * SO::width + 1) & ~(size_t)1));   // [nvars][EB_KB]
   for (int i = threadIdx.x; i < tsz * SO::width; i += blockDim.x) Ts[i] = T[i];
   const int kb0 = k0 + blockIdx.y * EB_KB;
   for (int e = threadIdx.x; e < EB_KB * g.nvars; e += blockDim.x) {
-    int kk = kb0 + e / g.nvars, d = e % g.nvars;
-    rowoff[e] = (kk < k1) ? toff_rows[d] + deg[(size_t)kk * g.nvars + d] * g.nq[d] : 0;
+    const int d = e / EB_KB, kk = kb0 + e % EB_KB;
+    rowoff[e] = (kk < k1) ? g.toff[d] + deg[(size_t)kk * g.nvars + d] * g.nq[d] : 0;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,24 +140,29 @@ __global__ void __launch_bounds__(EB_WARPS * 32) k_eval_basis_grid(GridParams g,
   for (int d = 0; d < g.nvars; d++) mybase[d] = (unsigned short)dg[d];
   const int nk = min(EB_KB, k1 - kb0);
   int kk = 0;
-  for (; kk + 4 <= nk; kk += 4) {                      // four independent product chains
-    S v0 = SO::from(1.0), v1 = v0, v2 = v0, v3 = v0;
-    const int *ro = rowoff + kk * g.nvars;
+  for (; kk + 8 <= nk; kk += 8) {                      // eight independent product chains
+    S v[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) v[c] = SO::from(1.0);
     for (int d = 0; d < g.nvars; d++) {
       const int dd = mybase[d];
-      v0 = s_mul(v0, SO::load(Ts, ro[d] + dd));
-      v1 = s_mul(v1, SO::load(Ts, ro[g.nvars + d] + dd));
-      v2 = s_mul(v2, SO::load(Ts, ro[2 * g.nvars + d] + dd));
-      v3 = s_mul(v3, SO::load(Ts, ro[3 * g.nvars + d] + dd));
+      const int4 ra = *reinterpret_cast<const int4 *>(rowoff + d * EB_KB + kk);
+      const int4 rb = *reinterpret_cast<const int4 *>(rowoff + d * EB_KB + kk + 4);
+      v[0] = s_mul(v[0], SO::load(Ts, ra.x + dd));
+      v[1] = s_mul(v[1], SO::load(Ts, ra.y + dd));
+      v[2] = s_mul(v[2], SO::load(Ts, ra.z + dd));
+      v[3] = s_mul(v[3], SO::load(Ts, ra.w + dd));
+      v[4] = s_mul(v[4], SO::load(Ts, rb.x + dd));
+      v[5] = s_mul(v[5], SO::load(Ts, rb.y + dd));
+      v[6] = s_mul(v[6], SO::load(Ts, rb.z + dd));
+      v[7] = s_mul(v[7], SO::load(Ts, rb.w + dd));
     }
-    SO::store(psi, (size_t)(kb0 + kk - k0) * nqr + r, v0);
-    SO::store(psi, (size_t)(kb0 + kk + 1 - k0) * nqr + r, v1);
-    SO::store(psi, (size_t)(kb0 + kk + 2 - k0) * nqr + r, v2);
-    SO::store(psi, (size_t)(kb0 + kk + 3 - k0) * nqr + r, v3);
+#pragma unroll
+    for (int c = 0; c < 8; c++) SO::store(psi, (size_t)(kb0 + kk + c - k0) * nqr + r, v[c]);
   }
   for (; kk < nk; kk++) {
     S v = SO::from(1.0);
-    for (int d = 0; d < g.nvars; d++) v = s_mul(v, SO::load(Ts, rowoff[kk * g.nvars + d] + mybase[d]));
+    for (int d = 0; d < g.nvars; d++) v = s_mul(v, SO::load(Ts, rowoff[d * EB_KB + kk] + mybase[d]));
     SO::store(psi, (size_t)(kb0 + kk - k0) * nqr + r, v);
   }
 }
@@ -205,7 +212,7 @@ void fill_tab(const pspace_ctx *c, TabParams &p) {
 void fill_grid(const pspace_ctx *c, GridParams &g) {
   g.nvars = c->nvars; g.DP = c->DP;
   for (int d = 0; d < c->nvars; d++) g.nq[d] = c->nq[d];
-  for (int d = 0; d <= c->nvars; d++) g.roff[d] = c->roff[d];
+  for (int d = 0; d <= c->nvars; d++) { g.roff[d] = c->roff[d]; g.toff[d] = c->toff[d]; }
 }
 }  // namespace
 
@@ -267,20 +274,17 @@ int ps_eval_basis_grid(const pspace_ctx *c, int k0, int k1, long long q0, long l
   if (k1 <= k0 || q1 <= q0) return PSPACE_OK;
   GridParams g;
   fill_grid(c, g);
-  int *d_toff = nullptr;
-  PS_CUDA(cudaMallocAsync(&d_toff, sizeof(int) * c->nvars, st));
-  PS_CUDA(cudaMemcpyAsync(d_toff, c->toff, sizeof(int) * c->nvars, cudaMemcpyHostToDevice, st));
   dim3 grid((unsigned)((q1 - q0 + EB_WARPS * 32 - 1) / (EB_WARPS * 32)), (unsigned)((k1 - k0 + EB_KB - 1) / EB_KB));
-  size_t smem = sizeof(double) * c->width * c->tsz + sizeof(int) * EB_KB * c->nvars + sizeof(unsigned short) * EB_WARPS * 32 * PSPACE_MAX_VARS;
+  size_t smem = sizeof(double) * (((size_t)c->width * c->tsz + 1) & ~(size_t)1) + sizeof(int) * EB_KB * c->nvars +
+                sizeof(unsigned short) * EB_WARPS * 32 * PSPACE_MAX_VARS;
   if (c->is_complex) {
     PS_CUDA(cudaFuncSetAttribute(k_eval_basis_grid<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_eval_basis_grid<cplx><<<grid, EB_WARPS * 32, smem, st>>>(g, c->tsz, c->d_T, d_toff, c->d_deg, k0, k1, q0, q1, c->d_qdig, psi);
+    k_eval_basis_grid<cplx><<<grid, EB_WARPS * 32, smem, st>>>(g, c->tsz, c->d_T, c->d_deg, k0, k1, q0, q1, c->d_qdig, psi);
   } else {
     PS_CUDA(cudaFuncSetAttribute(k_eval_basis_grid<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_eval_basis_grid<double><<<grid, EB_WARPS * 32, smem, st>>>(g, c->tsz, c->d_T, d_toff, c->d_deg, k0, k1, q0, q1, c->d_qdig, psi);
+    k_eval_basis_grid<double><<<grid, EB_WARPS * 32, smem, st>>>(g, c->tsz, c->d_T, c->d_deg, k0, k1, q0, q1, c->d_qdig, psi);
   }
   PS_LAUNCH_CHECK(c);
-  PS_CUDA(cudaFreeAsync(d_toff, st));
   return PSPACE_OK;
 }
 

@@ -269,7 +269,7 @@ def test_expansion_evaluation_vs_oracle(cplx):
           ("normal", -1.0, 0.4, 2)]
     o = H.CpuContainer(H.oracle_api(cplx), ps, 0).initialize()      # tensor basis: N = Q = 180
     c = _dc(ps, 0, cplx).initialize()
-    for m in (1, 3, 8, 24, 33, 70):
+    for m in (1, 3, 8, 24, 28, 33, 60, 70):          # every warp-tile width of k_expand
         V = rng.normal(size=(o.N, m)).astype(o.dtype)
         if cplx:
             V = V + 1j * rng.normal(size=V.shape)
@@ -285,6 +285,32 @@ def test_expansion_evaluation_vs_oracle(cplx):
         back = c.projectVector(U).cpu().numpy()
         assert normwise(back, V) < 1e-11, m
     c.close()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_basis_panel_is_bit_identical_to_batched_basis(cplx):
+    """The q-major panel kernel (k_psi_panel: prefix product over the slow variables kept per thread) must produce the
+    very values of the k-major batched evaluation (k_eval_basis_grid): expanding the identity returns the panel itself
+    (every sum has one non-zero term), for whole grids and for q-windows that start inside a prefix run."""
+    for ps, bt in (([("normal", 0.0, 1.0, 2), ("exponential", 0.0, 1.0, 0), ("uniform", -1.0, 1.0, 4), ("normal", 1.0, 2.0, 1)], 0),
+                   ([("uniform", 0.0, 1.0, 3), ("normal", 0.0, 1.0, 3), ("exponential", 0.5, 1.0, 0)], 1),
+                   ([("normal", 0.2, 0.7, 4)], 0),
+                   ([("uniform", 0.0, 1.0, 1)] * 6 + [("normal", 0.0, 1.0, 2)], 1)):
+        c = _dc(ps, bt, cplx).initialize()
+        dt = torch.complex128 if cplx else torch.float64
+        eye = torch.eye(c.N, dtype=dt, device="cuda")
+        psi = c.evalBasisGrid()                                  # [N][Q]
+        U = c.evaluateExpansion(eye)                             # [Q][N]
+
+        def same(a, b):      # real: pure products in the same order; complex: the panel kernel contracts to FMAs
+            return torch.equal(a, b) if not cplx else normwise(a.cpu().numpy(), b.cpu().numpy()) < 1e-14
+
+        assert same(U, psi.T.contiguous()), ps
+        for q0, q1 in ((1, c.Q), (c.Q // 3, c.Q - 1), (c.Q - 1, c.Q)):
+            for k0, k1 in ((0, c.N), (1, min(c.N, 3))):
+                Uw = c.evaluateExpansion(torch.eye(k1 - k0, dtype=dt, device="cuda"), k0, k1, q0, q1)
+                assert same(Uw, psi[k0:k1, q0:q1].T.contiguous()), (ps, q0, q1, k0, k1)
+        c.close()
 
 
 @pytest.mark.parametrize("cplx", [False, True])
