@@ -30,6 +30,8 @@ struct pspace_ctx {
   int DP = 16;                           // bytes per row of the digit table (16 or 32)
   uint8_t *d_qdig = nullptr;             // [Q][DP] mixed-radix digits of q (last variable fastest)
   double *d_W = nullptr;                 // [Q] scalars
+  size_t cap_rules = 0, cap_T = 0, cap_qdig = 0, cap_W = 0;   // bytes allocated (buffers are grow-only: re-initialising
+                                                              // with the same sizes does not touch the allocator)
   long long launches = 0;
   std::string plan;
   const char *plan_kernel = "";
@@ -63,6 +65,22 @@ int ps_fail(int code, const char *fmt, ...);
       return ps_fail(PSPACE_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
     if (ctxp) ((pspace_ctx *)(ctxp))->launches++;                                            \
   } while (0)
+
+// The last variable is the fastest index of the tensor grid, so the product over the leading variables [0, dsplit) is
+// shared by tail_stride consecutive points.  Picks the tail length (<= max_tail trailing variables) that minimises the
+// table reads per basis value, tail + (nvars - tail) / tail_stride.  Used by k_psi_panel and k_eval_basis_grid.
+static inline void ps_choose_tail(const pspace_ctx *c, int max_tail, int *dsplit, int *tail_stride) {
+  double best_cost = (double)c->nvars;
+  long long stride = 1;
+  *dsplit = c->nvars;
+  *tail_stride = 1;
+  for (int t = 1; t <= max_tail && t <= c->nvars; t++) {
+    stride *= c->nq[c->nvars - t];
+    if (stride > (1 << 20)) break;
+    const double cost = t + (double)(c->nvars - t) / (double)stride;
+    if (cost < best_cost) { best_cost = cost; *dsplit = c->nvars - t; *tail_stride = (int)stride; }
+  }
+}
 
 // implemented in basis.cu / tables.cu / project.cu, called from capi.cu
 int ps_basis_degrees_device(int nvars, const int *pmax, int basis_type, int *nbasis, int *d_out,

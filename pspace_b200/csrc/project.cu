@@ -826,7 +826,8 @@ __global__ void __launch_bounds__(256) k_tile_list(const unsigned char *mask, in
 }
 
 // Adds the stream-K pieces of each remainder tile in CTA order and stores the tile (guards, accumulate).
-// One block per remainder tile.  Geometry arguments restate k_project_ws's decomposition.
+// grid = (remainder tiles, element slices of a tile).  Geometry arguments restate k_project_ws's decomposition.
+constexpr int FIXUP_MAX_G = 1024;
 __global__ void __launch_bounds__(256) k_fixup(const __grid_constant__ ProjParams p, int G, int BM, int BN, int BI, int NJ,
                                                int matrix, int kq) {
   const int nchunk = (int)((p.q1 - p.q0 + kq - 1) / kq);
@@ -844,16 +845,27 @@ __global__ void __launch_bounds__(256) k_fixup(const __grid_constant__ ProjParam
   int g_lo = (int)((u0 * G) / rem_units);
   while (g_lo > 0 && rem_units * g_lo / G > u0) g_lo--;
   while (rem_units * (g_lo + 1) / G <= u0) g_lo++;
-  for (int e = threadIdx.x; e < BM * BN; e += blockDim.x) {
-    const int r = e / BN, cc = e % BN;
-    double sum = 0.0;
-    for (int g = g_lo; g < G; g++) {
+  // the workspace slots that hold pieces of this tile, in CTA order (block-uniform, computed once)
+  __shared__ int s_src[FIXUP_MAX_G];
+  __shared__ int s_n;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int g = g_lo; g < G && n < FIXUP_MAX_G; g++) {
       const long long a0 = rem_units * g / G, a1 = rem_units * (g + 1) / G;
       if (a0 >= u1) break;
       if (a1 <= a0) continue;
-      const int slot = (a0 / nchunk == rt) ? 0 : 1;
-      sum += p.sk_ws[((size_t)g * 2 + slot) * ((size_t)BM * BN) + e];
+      s_src[n++] = g * 2 + ((a0 / nchunk == rt) ? 0 : 1);
     }
+    s_n = n;
+  }
+  __syncthreads();
+  const int npieces = s_n;
+  // blockIdx.y splits the tile's elements, so that a few big remainder tiles still fill the machine
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < BM * BN; e += gridDim.y * blockDim.x) {
+    const int r = e / BN, cc = e % BN;
+    double sum = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < npieces; k++) sum += p.sk_ws[(size_t)s_src[k] * ((size_t)BM * BN) + e];
     if (p.peer_world > 0) {          // fused multi-GPU mode: the summed partial tile goes to its owner's receive slot
       const int pt = tile / p.tiles_n;
       const int owner = min(p.peer_world - 1, pt / p.peer_lp), lp = pt - owner * p.peer_lp;
@@ -977,19 +989,7 @@ int build_panels(pspace_ctx *c, const ProjParams &p, bool matrix, double **d_pi,
   pp.T = c->d_T; pp.deg = c->d_deg; pp.qdig = c->d_qdig; pp.W = c->d_W;
   for (int d = 0; d < c->nvars; d++) { pp.toff[d] = c->toff[d]; pp.nq[d] = c->nq[d]; }
   pp.q0 = p.q0; pp.q1 = p.q1;
-  // tail = the trailing variables whose digits change within a block of consecutive points: pick the length that
-  // minimises table reads per value, tail + (nvars - tail) / (points sharing a prefix)
-  {
-    double best_cost = (double)c->nvars;
-    long long stride = 1;
-    pp.dsplit = c->nvars; pp.tail_stride = 1;
-    for (int t = 1; t <= PSI_TAIL && t <= c->nvars; t++) {
-      stride *= c->nq[c->nvars - t];
-      if (stride > (1 << 20)) break;
-      const double cost = t + (double)(c->nvars - t) / (double)stride;
-      if (cost < best_cost) { best_cost = cost; pp.dsplit = c->nvars - t; pp.tail_stride = (int)stride; }
-    }
-  }
+  ps_choose_tail(c, PSI_TAIL, &pp.dsplit, &pp.tail_stride);
   const size_t smem = (size_t)(((c->tsz * W + 1) & ~1) + PSI_PTS * W) * 8 + (size_t)PSI_PTS * c->DP;
   for (int side = matrix ? 0 : 1; side < 2; side++) {
     pp.r0 = side ? p.j0 : p.i0; pp.nr = side ? p.nj : p.ni; pp.nr_pad = side ? *nj_pad : *ni_pad;
@@ -1104,7 +1104,9 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
     else k_project_ws<TL, EPI_DENSE><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
     PS_LAUNCH_CHECK(c);
     if (fix_blocks > 0) {
-      k_fixup<<<fix_blocks, 256, 0, st>>>(p, pl.sk_grid, TL::BM, TL::BN, TL::BI, TL::NJ, MAT ? 1 : 0, LY::KQW);
+      // ~2 blocks per SM in total, at least 256 elements per block
+      const int fix_split = std::max(1, std::min((TL::BM * TL::BN) / 256, (2 * pl.sk_grid + fix_blocks - 1) / fix_blocks));
+      k_fixup<<<dim3(fix_blocks, fix_split), 256, 0, st>>>(p, pl.sk_grid, TL::BM, TL::BN, TL::BI, TL::NJ, MAT ? 1 : 0, LY::KQW);
       PS_LAUNCH_CHECK(c);
     }
     if (d_list) PS_CUDA(cudaFreeAsync(d_list, st));
@@ -1152,8 +1154,10 @@ typedef Tile<4, 6, 4, 2, true, MODE_MATRIX, 4, 1> ZM96G;
 typedef Tile<4, 4, 4, 2, true, MODE_MATRIX, 4, 1> ZM64G;
 typedef Tile<2, 4, 8, 1, false, MODE_VECTOR, 4, 1> V32;     // 128 basis rows x 32 cols
 typedef Tile<2, 1, 8, 1, false, MODE_VECTOR, 4, 1> V8;
+typedef Tile<2, 3, 8, 1, false, MODE_VECTOR, 4, 1> V24;     // 128 x 24 (m = 24: one column tile, no padded columns)
 typedef Tile<2, 4, 8, 1, true, MODE_VECTOR, 4, 1> ZV32;
 typedef Tile<2, 1, 8, 1, true, MODE_VECTOR, 4, 1> ZV8;
+typedef Tile<2, 3, 8, 1, true, MODE_VECTOR, 4, 1> ZV24;
 
 const Variant MAT_VARIANTS[] = {{1, M96::BM, M96::BN, M96::BI, 8, 1, "dmma 128x96"},
                                 {2, M64::BM, M64::BN, M64::BI, 8, 1, "dmma 128x64"},
@@ -1162,7 +1166,8 @@ const Variant MAT_VARIANTS[] = {{1, M96::BM, M96::BN, M96::BI, 8, 1, "dmma 128x9
                                 {5, M96G::BM, M96G::BN, M96G::BI, 8, 1, "dmma 128x96 (4x2 warps)"},
                                 {6, M64G::BM, M64G::BN, M64G::BI, 8, 1, "dmma 128x64 (4x2 warps)"}};
 const Variant VEC_VARIANTS[] = {{1, V32::BM, V32::BN, 0, V32::BM, 1, "dmma vec 128x32"},
-                                {2, V8::BM, V8::BN, 0, V8::BM, 1, "dmma vec 128x8"}};
+                                {2, V8::BM, V8::BN, 0, V8::BM, 1, "dmma vec 128x8"},
+                                {3, V24::BM, V24::BN, 0, V24::BM, 1, "dmma vec 128x24"}};
 
 int sm_count(int device) {
   static int cached[64] = {0};
@@ -1181,22 +1186,28 @@ int make_plan(const pspace_ctx *c, int is_matrix, const pspace_project_args *a, 
   if (is_matrix && (a->j0 < 0 || a->j1 > c->N || a->j1 < a->j0)) return ps_fail(PSPACE_EINVAL, "j range [%d,%d) outside [0,%d)", a->j0, a->j1, c->N);
   const int ncols_d = a->ncols * c->width;
   const Variant *vs = is_matrix ? MAT_VARIANTS : VEC_VARIANTS;
-  const int nv = is_matrix ? 6 : 2;
-  const int nauto = is_matrix ? 4 : 2;   // variants considered by the automatic choice
+  const int nv = is_matrix ? 6 : 3;
+  const int nauto = is_matrix ? 4 : 3;   // variants considered by the automatic choice
   int best = -1;
   if (a->variant > 0) {
     for (int i = 0; i < nv; i++) if (vs[i].id == a->variant) best = i;
     if (best < 0) return ps_fail(PSPACE_EINVAL, "unknown tile variant %d", a->variant);
   } else {
     double bestcost = 0;
+    int besttn = 0;
     for (int i = 0; i < nauto; i++) {
       // padded work; ties go to the earlier (wider) variant
-      double padn = (double)((ncols_d + vs[i].BN - 1) / vs[i].BN) * vs[i].BN;
+      const int tn = (ncols_d + vs[i].BN - 1) / vs[i].BN;
+      double padn = (double)tn * vs[i].BN;
       double padm;
       if (is_matrix) padm = (double)((a->k1 - a->k0 + vs[i].BI - 1) / vs[i].BI) * vs[i].BI * ((a->j1 - a->j0 + 7) / 8) * 8;
       else padm = (double)((a->k1 - a->k0 + vs[i].BM - 1) / vs[i].BM) * vs[i].BM;
       double cost = padn * padm;
-      if (best < 0 || cost < bestcost * 0.999) { best = i; bestcost = cost; }
+      // the vector projection is bound by streaming the basis panel, which every column tile reads again:
+      // fewest column tiles first, padded work second
+      const bool better = is_matrix ? cost < bestcost * 0.999
+                                    : (tn < besttn || (tn == besttn && cost < bestcost * 0.999));
+      if (best < 0 || better) { best = i; bestcost = cost; besttn = tn; }
     }
   }
   const Variant &v = vs[best];
@@ -1384,8 +1395,10 @@ int ps_project_ex(const pspace_ctx *c, int is_matrix, const pspace_project_args 
     case 16: rc = launch<ZM64G>(c, p, pl, a, d_out, d_ws, st); break;
     case 101: rc = launch<V32>(c, p, pl, a, d_out, d_ws, st); break;
     case 102: rc = launch<V8>(c, p, pl, a, d_out, d_ws, st); break;
+    case 103: rc = launch<V24>(c, p, pl, a, d_out, d_ws, st); break;
     case 111: rc = launch<ZV32>(c, p, pl, a, d_out, d_ws, st); break;
     case 112: rc = launch<ZV8>(c, p, pl, a, d_out, d_ws, st); break;
+    case 113: rc = launch<ZV24>(c, p, pl, a, d_out, d_ws, st); break;
     default: rc = ps_fail(PSPACE_EINVAL, "no kernel for key %d", key);
   }
   if (rc) return rc;

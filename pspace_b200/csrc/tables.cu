@@ -227,12 +227,21 @@ int ps_build_tables(pspace_ctx *c, cudaStream_t st) {
   const bool with_tables = c->basis_ready;
   for (int d = 0; d < c->nvars; d++) { c->toff[d] = c->tsz; if (with_tables) c->tsz += (c->pmax[d] + 1) * c->nq[d]; }
   c->toff[c->nvars] = c->tsz;
-  if (c->d_zp) { PS_CUDA(cudaFree(c->d_zp)); PS_CUDA(cudaFree(c->d_yp)); PS_CUDA(cudaFree(c->d_wp)); c->d_zp = nullptr; }
-  if (c->d_T) { PS_CUDA(cudaFree(c->d_T)); c->d_T = nullptr; }
-  PS_CUDA(cudaMalloc(&c->d_zp, sizeof(double) * w * sumnq));
-  PS_CUDA(cudaMalloc(&c->d_yp, sizeof(double) * w * sumnq));
-  PS_CUDA(cudaMalloc(&c->d_wp, sizeof(double) * w * sumnq));
-  if (with_tables) PS_CUDA(cudaMalloc(&c->d_T, sizeof(double) * w * (c->tsz > 0 ? c->tsz : 1)));
+  const size_t need_rules = sizeof(double) * w * sumnq, need_T = sizeof(double) * w * (c->tsz > 0 ? c->tsz : 1);
+  if (need_rules > c->cap_rules) {
+    if (c->d_zp) { PS_CUDA(cudaFree(c->d_zp)); PS_CUDA(cudaFree(c->d_yp)); PS_CUDA(cudaFree(c->d_wp)); c->d_zp = c->d_yp = c->d_wp = nullptr; }
+    c->cap_rules = 0;
+    PS_CUDA(cudaMalloc(&c->d_zp, need_rules));
+    PS_CUDA(cudaMalloc(&c->d_yp, need_rules));
+    PS_CUDA(cudaMalloc(&c->d_wp, need_rules));
+    c->cap_rules = need_rules;
+  }
+  if (with_tables && need_T > c->cap_T) {
+    if (c->d_T) { PS_CUDA(cudaFree(c->d_T)); c->d_T = nullptr; }
+    c->cap_T = 0;
+    PS_CUDA(cudaMalloc(&c->d_T, need_T));
+    c->cap_T = need_T;
+  }
   TabParams p;
   fill_tab(c, p);
   if (c->is_complex) k_rules_tables<cplx><<<c->nvars, 128, 0, st>>>(p, c->d_zp, c->d_yp, c->d_wp, c->d_T, with_tables);
@@ -246,10 +255,19 @@ int ps_build_tables(pspace_ctx *c, cudaStream_t st) {
 int ps_build_grid(pspace_ctx *c, cudaStream_t st) {
   const int w = c->width;
   c->DP = c->nvars <= 16 ? 16 : 32;
-  if (c->d_qdig) { PS_CUDA(cudaFree(c->d_qdig)); c->d_qdig = nullptr; }
-  if (c->d_W) { PS_CUDA(cudaFree(c->d_W)); c->d_W = nullptr; }
-  PS_CUDA(cudaMalloc(&c->d_qdig, (size_t)c->Q * c->DP));
-  PS_CUDA(cudaMalloc(&c->d_W, sizeof(double) * w * (size_t)c->Q));
+  const size_t need_dig = (size_t)c->Q * c->DP, need_W = sizeof(double) * w * (size_t)c->Q;
+  if (need_dig > c->cap_qdig) {
+    if (c->d_qdig) { PS_CUDA(cudaFree(c->d_qdig)); c->d_qdig = nullptr; }
+    c->cap_qdig = 0;
+    PS_CUDA(cudaMalloc(&c->d_qdig, need_dig));
+    c->cap_qdig = need_dig;
+  }
+  if (need_W > c->cap_W) {
+    if (c->d_W) { PS_CUDA(cudaFree(c->d_W)); c->d_W = nullptr; }
+    c->cap_W = 0;
+    PS_CUDA(cudaMalloc(&c->d_W, need_W));
+    c->cap_W = need_W;
+  }
   GridParams g;
   fill_grid(c, g);
   unsigned nb = (unsigned)((c->Q + 255) / 256);

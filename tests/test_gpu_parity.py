@@ -225,7 +225,7 @@ def test_every_tile_variant_matches():
         C = c.projectMatrix(Jd, 0, 20, 3, 30, variant=variant).cpu().numpy()
         assert normwise(C, ref) < TOL, variant
     refF = o.project_vector(J)
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         F = c.projectVector(Jd, variant=variant).cpu().numpy()
         assert normwise(F, refF) < TOL, variant
     c.close()

@@ -43,6 +43,7 @@ def main():
     except Exception:
         hbm, src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     c = D.DeviceContainer(w.params, w.basis_type, w.complex_).initialize()
+    c.setOption("panel_cache", 0)     # every call rebuilds its basis panel (as bench.py does): no work carried between calls
     o = H.CpuContainer(H.oracle_api(w.complex_), w.params, w.basis_type).initialize()
     N, Q, nv, m = c.N, c.Q, c.nvars, w.m
     wd = 2 if w.complex_ else 1
