@@ -295,7 +295,8 @@ def test_basis_panel_is_bit_identical_to_batched_basis(cplx):
     for ps, bt in (([("normal", 0.0, 1.0, 2), ("exponential", 0.0, 1.0, 0), ("uniform", -1.0, 1.0, 4), ("normal", 1.0, 2.0, 1)], 0),
                    ([("uniform", 0.0, 1.0, 3), ("normal", 0.0, 1.0, 3), ("exponential", 0.5, 1.0, 0)], 1),
                    ([("normal", 0.2, 0.7, 4)], 0),
-                   ([("uniform", 0.0, 1.0, 1)] * 6 + [("normal", 0.0, 1.0, 2)], 1)):
+                   ([("uniform", 0.0, 1.0, 1)] * 6 + [("normal", 0.0, 1.0, 2)], 1),
+                   ([("normal", 0.0, 1.0, 8), ("exponential", 0.0, 1.0, 8), ("uniform", 0.0, 1.0, 8)], 0)):   # N = 729 > 512 rows
         c = _dc(ps, bt, cplx).initialize()
         dt = torch.complex128 if cplx else torch.float64
         eye = torch.eye(c.N, dtype=dt, device="cuda")
@@ -339,6 +340,56 @@ def test_tacs_layouts_and_pair_mask_bit_exact(cplx):
         assert same_bits(pq, np.ascontiguousarray(F.T).ravel())
     for dmapf in ([3, 3, 3], [1, 0, 1], [0, 0, 0], [2, 1, 0]):
         assert np.array_equal(c.pairMask(dmapf).cpu().numpy(), H.pair_mask(o.degrees(), dmapf)), dmapf
+    c.close()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_adjoint_residual_product_composition_vs_reference_loop(cplx):
+    """(f4) TACSStochasticElement::addAdjResProduct (TACSStochasticElement.cpp:548-637): for every quadrature point the
+    reference rebuilds the deterministic states u_q and adjoint psi_q from the TACS-interleaved stochastic vectors
+    (getDeterministicStates / getDeterministicAdjoint, :53-120) and adds wt*scale*g(psi_q, u_q, y_q) with
+    wt = basis(0, z_q) * w_q.  On the device this is gather -> two expansion evaluations -> the caller's product
+    (here a synthetic deterministic element) -> vector projection onto basis row 0.  The CPU side below is the
+    reference loop, quadrature point by quadrature point, over the oracle's basis()/quadrature() values."""
+    from pspace_b200 import device as D
+    rng = np.random.default_rng(77 + cplx)
+    ps = [("normal", 0.3 + (1e-30j if cplx else 0), 1.2, 3), ("uniform", -1.0, 2.0, 2), ("exponential", 0.0, 0.5, 2)]
+    o = H.CpuContainer(H.oracle_api(cplx), ps, 1).initialize()
+    c = _dc(ps, 1, cplx).initialize()
+    N, Q, nv = o.N, o.Q, len(ps)
+    nnodes, ndvpn, dvlen, scale = 3, 2, 5, 0.75
+    m, nsvpn = nnodes * ndvpn, N * ndvpn
+
+    def rnd(n):
+        a = rng.normal(size=n).astype(o.dtype)
+        return a + 1j * rng.normal(size=n) if cplx else a
+
+    v, adj = rnd(N * m), rnd(N * m)                 # TACS layout: [node][basis term][dof]
+    Zo, Yo, Wo = o.grid()
+    psi = o.basis_at(Zo)                            # [N][Q]
+
+    def element_product(pq, uq, yq):                # synthetic deterministic addAdjResProduct: dvLen values per point
+        return np.array([np.sum(pq * uq) * (1.0 + 0.1 * n) + yq[n % nv] * np.sum(uq) for n in range(dvlen)])
+
+    dfdx_ref = np.zeros(dvlen, dtype=o.dtype)
+    for q in range(Q):                              # :585-607
+        wt = psi[0, q] * Wo[q]
+        uq, pq = np.zeros(m, dtype=o.dtype), np.zeros(m, dtype=o.dtype)
+        for n in range(nnodes):                     # :84-120  u_q[n*ndvpn+d] = sum_k psi_k(z_q) v[n*nsvpn + k*ndvpn + d]
+            for k in range(N):
+                for d in range(ndvpn):
+                    uq[n * ndvpn + d] += psi[k, q] * v[n * nsvpn + k * ndvpn + d]
+                    pq[n * ndvpn + d] += psi[k, q] * adj[n * nsvpn + k * ndvpn + d]
+        dfdx_ref += wt * scale * element_product(pq, uq, Yo[q])
+
+    V = D.gather_vector_tacs(torch.from_numpy(v).cuda(), N, nnodes, ndvpn)
+    A = D.gather_vector_tacs(torch.from_numpy(adj).cuda(), N, nnodes, ndvpn)
+    U, P = c.evaluateExpansion(V), c.evaluateExpansion(A)               # [Q][m] each
+    _, Y, _ = c.grid()
+    su, spu = U.sum(dim=1), (P * U).sum(dim=1)
+    G = torch.stack([spu * (1.0 + 0.1 * n) + Y[:, n % nv] * su for n in range(dvlen)], dim=1).contiguous()
+    dfdx = scale * c.projectVector(G, 0, 1)[0]                          # basis row 0 only (:583)
+    assert normwise(dfdx.cpu().numpy(), dfdx_ref) < TOL
     c.close()
 
 
