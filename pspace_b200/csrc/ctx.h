@@ -35,6 +35,7 @@ struct pspace_ctx {
   long long launches = 0;
   std::string plan;
   const char *plan_kernel = "";
+  int plan_chunk_pts = 32;               // quadrature points per pipeline stage of the kernel that ran
   void *d_panel = nullptr;               // basis panels of the last project call (see project.cu build_panels)
   size_t panel_bytes = 0;
   long long panel_key[7] = {0};

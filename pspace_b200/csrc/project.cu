@@ -1111,6 +1111,7 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
     }
     if (d_list) PS_CUDA(cudaFreeAsync(d_list, st));
     mc->plan_kernel = "tma+mbarrier warp-specialised, persistent stream-K";
+    mc->plan_chunk_pts = LY::KQW;
     return PSPACE_OK;
   }
   size_t smem = TL::smem_bytes(c->tsz, c->nvars);
@@ -1134,6 +1135,7 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
     PS_LAUNCH_CHECK(c);
   }
   mc->plan_kernel = "cp.async all-warps";
+  mc->plan_chunk_pts = KQ;
   return PSPACE_OK;
 }
 
@@ -1408,7 +1410,8 @@ int ps_project_ex(const pspace_ctx *c, int is_matrix, const pspace_project_args 
   mc->plan_flop = 2.0 * rows * (double)ncols_d * (double)(a->q1 - a->q0) * (c->is_complex ? 2.0 : 1.0);   // useful (all ordered pairs)
   char buf[256];
   snprintf(buf, sizeof buf, "%s%s [%s] tiles=%dx%dx%d chunks=%lld ctas=%d streamk_tiles=%d ksplit(generic)=%d", c->is_complex ? "z " : "",
-           v.name, c->plan_kernel, pl.tiles_i, pl.tiles_j, pl.tiles_n, pl.nchunk, pl.sk_grid, pl.sk_rem_tiles, pl.ksplit);
+           v.name, c->plan_kernel, pl.tiles_i, pl.tiles_j, pl.tiles_n,
+           (long long)((a->q1 - a->q0 + c->plan_chunk_pts - 1) / c->plan_chunk_pts), pl.sk_grid, pl.sk_rem_tiles, pl.ksplit);
   mc->plan = buf;
   return PSPACE_OK;
 }
