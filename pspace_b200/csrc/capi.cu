@@ -69,7 +69,7 @@ int pspace_cuda_destroy(pspace_ctx *c) {
   cudaSetDevice(c->device);
   cudaFree(c->d_deg); cudaFree(c->d_zp); cudaFree(c->d_yp); cudaFree(c->d_wp); cudaFree(c->d_T);
   cudaFree(c->d_qdig); cudaFree(c->d_W);
-  cudaFree(c->d_panel);
+  cudaFree(c->panel_u.d); cudaFree(c->panel_w.d);
   cudaFree(c->d_scratch_in); cudaFree(c->d_scratch_out); cudaFree(c->d_scratch_ws);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->copy_stream) {
@@ -111,7 +111,7 @@ int pspace_cuda_initialize_basis(pspace_ctx *c, const int *pmax, void *stream) {
   PS_CUDA(cudaMemcpyAsync(c->h_deg.data(), c->d_deg, sizeof(int) * c->h_deg.size(), cudaMemcpyDeviceToHost, st));
   PS_CUDA(cudaStreamSynchronize(st));
   c->basis_ready = true;
-  c->panel_valid = false;
+  c->invalidate_panels();
   return ps_build_tables(c, st);
 }
 
@@ -128,7 +128,7 @@ int pspace_cuda_initialize_quadrature(pspace_ctx *c, const int *nqpts, void *str
   for (int d = 0; d < c->nvars; d++) c->nq[d] = nqpts[d];
   c->Q = Q;
   c->quad_ready = true;
-  c->panel_valid = false;
+  c->invalidate_panels();
   int rc = ps_build_tables(c, st);
   if (rc) return rc;
   rc = ps_build_grid(c, st);
@@ -282,7 +282,7 @@ int pspace_cuda_project_matrix_batched(const pspace_ctx *c, const pspace_project
                     ws_bytes, (cudaStream_t)stream);
   }
   mc->panel_cache = saved;
-  if (!saved) mc->panel_valid = false;
+  if (!saved) mc->invalidate_panels();
   return rc;
 }
 
@@ -403,7 +403,7 @@ int pspace_cuda_set_option(pspace_ctx *c, const char *name, int value) {
   if (!c || !name) return ps_fail(PSPACE_EINVAL, "null argument");
   if (!strcmp(name, "force_generic")) { c->force_generic = value; return PSPACE_OK; }
   if (!strcmp(name, "slab_mb")) { c->slab_bytes = (long long)value << 20; return PSPACE_OK; }
-  if (!strcmp(name, "panel_cache")) { c->panel_cache = value; c->panel_valid = false; return PSPACE_OK; }
+  if (!strcmp(name, "panel_cache")) { c->panel_cache = value; c->invalidate_panels(); return PSPACE_OK; }
   return ps_fail(PSPACE_EINVAL, "unknown option %s", name);
 }
 

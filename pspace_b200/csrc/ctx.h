@@ -36,11 +36,20 @@ struct pspace_ctx {
   std::string plan;
   const char *plan_kernel = "";
   int plan_chunk_pts = 32;               // quadrature points per pipeline stage of the kernel that ran
-  void *d_panel = nullptr;               // basis panels of the last project call (see project.cu build_panels)
-  size_t panel_bytes = 0;
-  long long panel_key[7] = {0};
-  bool panel_valid = false;
-  int panel_cache = 1;                   // reuse the panels when the (window, q-range) of a call repeats
+  // Basis panels (project.cu ensure_panel): one slot for the unweighted rows psi_r(z_q) — the i side of the matrix
+  // projection and the left operand of the expansion — and one for the weighted rows w_q psi_r(z_q) — the j side of
+  // both projections.  Grow-only buffers; a slot is reused when its (row range, q-range) repeats, so a time-stepping
+  // loop of expand -> caller -> project builds each panel once.
+  struct PanelSlot {
+    double *d = nullptr;
+    size_t bytes = 0;
+    bool valid = false;
+    int r0 = 0, nr = 0;
+    long long q0 = 0, q1 = 0;
+  };
+  PanelSlot panel_u, panel_w;
+  void invalidate_panels() { panel_u.valid = panel_w.valid = false; }
+  int panel_cache = 1;                   // reuse a panel when the (row range, q-range) of a call repeats
   int force_generic = 0;                 // tests: force the cp.async kernel even where TMA is usable
   double plan_flop = 0.0;
   // scratch owned by the context for the host-buffer entry points

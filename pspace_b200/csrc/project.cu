@@ -961,55 +961,60 @@ int make_tmap(CUtensorMap *tm, const double *base, int rank, const unsigned long
   return PSPACE_OK;
 }
 
-// basis panels of a call, kept in the context (grow-only buffer, reused when the ranges repeat)
-int build_panels(pspace_ctx *c, const ProjParams &p, bool matrix, double **d_pi, double **d_pj, int *ni_pad,
-                 int *nj_pad, cudaStream_t st) {
+// One basis panel (rows [r0, r0+nr) over [q0,q1), weighted or not) in its context slot: grow-only buffer, rebuilt
+// unless the cache is on and the slot already holds exactly this panel.
+int ensure_panel(pspace_ctx *c, bool weighted, int r0, int nr, long long q0, long long q1, double **d_out, int *nr_pad,
+                 cudaStream_t st) {
+  pspace_ctx::PanelSlot &s = weighted ? c->panel_w : c->panel_u;
   const int W = c->width;
-  const long long nq = p.q1 - p.q0;
-  *ni_pad = matrix ? ((p.ni + 1) & ~1) : 0;
-  *nj_pad = (p.nj + 1) & ~1;
-  const size_t bytes_i = (size_t)W * nq * *ni_pad * 8, bytes_j = (size_t)W * nq * *nj_pad * 8;
-  const size_t off_j = (bytes_i + 255) & ~(size_t)255;
-  const size_t need = off_j + bytes_j;
-  const bool same = c->panel_cache && c->panel_valid && c->panel_key[0] == p.i0 && c->panel_key[1] == p.ni &&
-                    c->panel_key[2] == p.j0 && c->panel_key[3] == p.nj && c->panel_key[4] == p.q0 &&
-                    c->panel_key[5] == p.q1 && c->panel_key[6] == (matrix ? 1 : 0);
-  if (need > c->panel_bytes) {
-    if (c->d_panel) { PS_CUDA(cudaStreamSynchronize(st)); PS_CUDA(cudaFree(c->d_panel)); c->d_panel = nullptr; c->panel_bytes = 0; }
-    cudaError_t e = cudaMalloc(&c->d_panel, need);
+  const long long nq = q1 - q0;
+  *nr_pad = (nr + 1) & ~1;
+  const size_t need = (size_t)W * nq * *nr_pad * 8;
+  if (need > s.bytes) {
+    if (s.d) { PS_CUDA(cudaStreamSynchronize(st)); PS_CUDA(cudaFree(s.d)); s.d = nullptr; s.bytes = 0; }
+    s.valid = false;
+    cudaError_t e = cudaMalloc(&s.d, need);
     if (e != cudaSuccess) return ps_fail(PSPACE_ENOMEM, "basis panel of %zu bytes: %s", need, cudaGetErrorString(e));
-    c->panel_bytes = need;
-    c->panel_valid = false;
+    s.bytes = need;
   }
-  *d_pi = reinterpret_cast<double *>(c->d_panel);
-  *d_pj = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(c->d_panel) + off_j);
-  if (same && c->panel_valid) return PSPACE_OK;
+  *d_out = s.d;
+  if (need == 0) return PSPACE_OK;
+  if (c->panel_cache && s.valid && s.r0 == r0 && s.nr == nr && s.q0 == q0 && s.q1 == q1) return PSPACE_OK;
+  s.valid = false;
   PanelParams pp;
   pp.nvars = c->nvars; pp.tsz = c->tsz; pp.DP = c->DP; pp.width = W;
   pp.T = c->d_T; pp.deg = c->d_deg; pp.qdig = c->d_qdig; pp.W = c->d_W;
   for (int d = 0; d < c->nvars; d++) { pp.toff[d] = c->toff[d]; pp.nq[d] = c->nq[d]; }
-  pp.q0 = p.q0; pp.q1 = p.q1;
+  pp.q0 = q0; pp.q1 = q1;
   ps_choose_tail(c, PSI_TAIL, &pp.dsplit, &pp.tail_stride);
+  pp.r0 = r0; pp.nr = nr; pp.nr_pad = *nr_pad;
+  pp.weighted = weighted ? 1 : 0; pp.out = s.d;
   const size_t smem = (size_t)(((c->tsz * W + 1) & ~1) + PSI_PTS * W) * 8 + (size_t)PSI_PTS * c->DP;
-  for (int side = matrix ? 0 : 1; side < 2; side++) {
-    pp.r0 = side ? p.j0 : p.i0; pp.nr = side ? p.nj : p.ni; pp.nr_pad = side ? *nj_pad : *ni_pad;
-    pp.weighted = side; pp.out = side ? *d_pj : *d_pi;
-    if (pp.nr_pad == 0) continue;
-    const int nt = std::min(PSI_MAXT, (pp.nr_pad + 31) & ~31);
-    const dim3 grid((unsigned)((nq + PSI_PTS - 1) / PSI_PTS), (unsigned)((pp.nr_pad + nt - 1) / nt));
-    if (c->is_complex) {
-      PS_CUDA(cudaFuncSetAttribute(k_psi_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_psi_panel<true><<<grid, nt, smem, st>>>(pp);
-    } else {
-      PS_CUDA(cudaFuncSetAttribute(k_psi_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_psi_panel<false><<<grid, nt, smem, st>>>(pp);
-    }
-    PS_LAUNCH_CHECK(c);
+  const int nt = std::min(PSI_MAXT, (pp.nr_pad + 31) & ~31);
+  const dim3 grid((unsigned)((nq + PSI_PTS - 1) / PSI_PTS), (unsigned)((pp.nr_pad + nt - 1) / nt));
+  if (c->is_complex) {
+    PS_CUDA(cudaFuncSetAttribute(k_psi_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_psi_panel<true><<<grid, nt, smem, st>>>(pp);
+  } else {
+    PS_CUDA(cudaFuncSetAttribute(k_psi_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_psi_panel<false><<<grid, nt, smem, st>>>(pp);
   }
-  c->panel_key[0] = p.i0; c->panel_key[1] = p.ni; c->panel_key[2] = p.j0; c->panel_key[3] = p.nj;
-  c->panel_key[4] = p.q0; c->panel_key[5] = p.q1; c->panel_key[6] = matrix ? 1 : 0;
-  c->panel_valid = true;
+  PS_LAUNCH_CHECK(c);
+  s.r0 = r0; s.nr = nr; s.q0 = q0; s.q1 = q1;
+  s.valid = true;
   return PSPACE_OK;
+}
+
+// basis panels of a projection call: Pi (unweighted, matrix mode only) and Pj (weighted)
+int build_panels(pspace_ctx *c, const ProjParams &p, bool matrix, double **d_pi, double **d_pj, int *ni_pad,
+                 int *nj_pad, cudaStream_t st) {
+  *ni_pad = 0;
+  *d_pi = nullptr;
+  if (matrix) {
+    int rc = ensure_panel(c, false, p.i0, p.ni, p.q0, p.q1, d_pi, ni_pad, st);
+    if (rc) return rc;
+  }
+  return ensure_panel(c, true, p.j0, p.nj, p.q0, p.q1, d_pj, nj_pad, st);
 }
 
 // sums the ksplit partial windows in slice order (deterministic) into the output
@@ -1248,30 +1253,10 @@ int make_plan(const pspace_ctx *c, int is_matrix, const pspace_project_args *a, 
 }
 }  // namespace
 
-// Unweighted / weighted basis panel of rows [r0, r0+nr) over [q0,q1) in the context's panel buffer (used by
-// expand.cu).  Invalidates the projection panel cache (same buffer).
+// Unweighted / weighted basis panel of rows [r0, r0+nr) over [q0,q1) in the context's panel slot (used by expand.cu)
 int ps_build_panel_rows(pspace_ctx *c, int r0, int nr, long long q0, long long q1, int weighted, double **d_panel,
                         int *nr_pad, cudaStream_t st) {
-  ProjParams p;
-  p.i0 = 0; p.ni = 0; p.j0 = r0; p.nj = nr; p.q0 = q0; p.q1 = q1;
-  double *d_pi = nullptr, *d_pj = nullptr;
-  int ni_pad = 0;
-  const int saved_cache = c->panel_cache;
-  c->panel_cache = 0;
-  c->panel_valid = false;
-  int rc;
-  if (weighted) rc = build_panels(c, p, false, &d_pi, &d_pj, &ni_pad, nr_pad, st);
-  else {
-    // the i side of build_panels is the unweighted one
-    p.i0 = r0; p.ni = nr; p.j0 = 0; p.nj = 0;
-    int nj_pad = 0;
-    rc = build_panels(c, p, true, &d_pi, &d_pj, nr_pad, &nj_pad, st);
-    d_pj = d_pi;
-  }
-  c->panel_cache = saved_cache;
-  c->panel_valid = false;
-  *d_panel = d_pj;
-  return rc;
+  return ensure_panel(c, weighted != 0, r0, nr, q0, q1, d_panel, nr_pad, st);
 }
 
 size_t ps_project_workspace(const pspace_ctx *c, int is_matrix, const pspace_project_args *a) {

@@ -344,6 +344,48 @@ def test_tacs_layouts_and_pair_mask_bit_exact(cplx):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
+def test_panel_cache_slots_reuse_and_invalidate(cplx):
+    """The two panel slots (unweighted rows: expansion + i side; weighted rows: j side) are reused when a call repeats
+    their (row range, q-range) and rebuilt otherwise: an interleaved sequence of expansions, vector and matrix
+    projections with the cache on must return bit-for-bit what the same calls return with the cache off, also across
+    a re-initialisation of the quadrature."""
+    rng = np.random.default_rng(91)
+    ps = [("normal", 0.3 + (1e-30j if cplx else 0), 1.2, 3), ("exponential", 0.0, 0.5, 2), ("uniform", -1.0, 2.0, 3)]
+    c = _dc(ps, 0, cplx).initialize()
+    dt = torch.complex128 if cplx else torch.float64
+
+    def operands():
+        V = torch.randn((c.N, 6), dtype=torch.float64, device="cuda").to(dt)
+        J = torch.randn((c.Q, 16), dtype=torch.float64, device="cuda").to(dt)
+        return V, J
+
+    def sequence(V, J):
+        q0, q1 = 5, c.Q - 3
+        out = []
+        for rep in range(2):
+            out.append(c.evaluateExpansion(V))                                            # U slot: all rows, all q
+            out.append(c.projectMatrix(J, 0, c.N, 2, 20))                                 # U hit, W built
+            out.append(c.projectVector(J, 2, 20))                                         # W hit
+            out.append(c.projectVector(J))                                                # W replaced
+            out.append(c.projectMatrix(J[q0:q1].contiguous(), 3, 11, 0, c.N, q0=q0, q1=q1))   # both replaced (q-window)
+            out.append(c.evaluateExpansion(V[3:11].contiguous(), 3, 11, q0, q1))          # U hit
+            out.append(c.projectMatrix(J, 0, c.N, 2, 20))                                 # both rebuilt
+        return [o.clone() for o in out]
+
+    for nq in (None, [5, 4, 6]):
+        if nq is not None:
+            c.initializeQuadrature(nq)           # new grid: every cached panel is stale
+        V, J = operands()
+        c.setOption("panel_cache", 0)
+        ref = sequence(V, J)
+        c.setOption("panel_cache", 1)
+        got = sequence(V, J)
+        for k, (a, b) in enumerate(zip(ref, got)):
+            assert torch.equal(a, b), (nq, k)
+    c.close()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
 def test_adjoint_residual_product_composition_vs_reference_loop(cplx):
     """(f4) TACSStochasticElement::addAdjResProduct (TACSStochasticElement.cpp:548-637): for every quadrature point the
     reference rebuilds the deterministic states u_q and adjoint psi_q from the TACS-interleaved stochastic vectors

@@ -94,6 +94,20 @@ def main():
     ms = gpu_time(lambda: c.projectVector(f, out=F))
     add("project_vector (a8)", ms, 8.0 * wd * (m * Q + 2 * N * Q), float(N) * Q, "(k,q) updates/s",
         note="bytes = f read, weighted panel written + read")
+    # the same two calls inside a time-stepping loop (expand -> caller -> project, same ranges every step): the
+    # unweighted and the weighted panel each stay in their context slot, so a step only reads them
+    c.setOption("panel_cache", 1)
+    c.evaluateExpansion(V, out=U)
+    c.projectVector(f, out=F)
+
+    def step():
+        c.evaluateExpansion(V, out=U)
+        c.projectVector(f, out=F)
+
+    ms = gpu_time(step)
+    add("evaluate_expansion + project_vector, cached panels (f1+a8)", ms, 8.0 * wd * (2 * N * Q + 2 * m * Q), 2.0 * N * Q,
+        "(k,q) terms/s", note="one step of a loop that repeats its ranges: bytes = both panels read once, U written, f read")
+    c.setOption("panel_cache", 0)
     # (f3) moments
     ms = gpu_time(lambda: c.moments(f))
     fh = f[:min(Q, 1 << 16)].cpu().numpy()
