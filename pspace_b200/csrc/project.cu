@@ -1078,7 +1078,8 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
       unsigned box[3] = {(unsigned)TL::BIP, (unsigned)LY::KQW, (unsigned)TL::W};
       if ((rc = make_tmap(&tmI, d_pi, 3, dims, str, box))) return rc;
     } else tmI = tmJ;
-    static bool attr_ws = false;
+    static bool attr_ws_dev[64] = {false};   // per instantiation and device (function attributes are per device)
+    bool &attr_ws = attr_ws_dev[c->device & 63];
     if (!attr_ws) {
       PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       if (MAT) {
@@ -1121,7 +1122,8 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
   }
   size_t smem = TL::smem_bytes(c->tsz, c->nvars);
   if (smem > 227 * 1024) return ps_fail(PSPACE_EINVAL, "1-D tables too large for the staged kernel (%zu B shared memory)", smem);
-  static bool attr_set = false;   // per instantiation
+  static bool attr_set_dev[64] = {false};   // per instantiation and device
+  bool &attr_set = attr_set_dev[c->device & 63];
   if (!attr_set) {
     PS_CUDA(cudaFuncSetAttribute(k_project<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
