@@ -186,3 +186,17 @@ def test_dense_dmma_loop_keeps_the_fast_ptxas_schedule():
     assert m, out
     assert int(m.group(1)) == 384                      # 16 k-steps (64-point stage) x 2 row tiles x 12 column tiles
     assert int(m.group(2)) <= 6290, out                # 384 x 16 = 6144 is the floor; 6256 today (the slower schedule: >= 6300)
+
+
+def test_cpp_caller_example_builds_against_the_reference_headers():
+    """examples/stochastic_element.cpp — a caller shaped like the reference's TACSStochasticElement — compiles and links
+    against host/include + libpspace.so in both scalar builds, and (no CPU path) aborts loudly without a GPU."""
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "examples"), "-B"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for exe in ("stochastic_element", "stochastic_element_z"):
+        path = os.path.join(ROOT, "examples", exe)
+        assert os.path.exists(path)
+        import torch
+        if not torch.cuda.is_available():
+            run = subprocess.run([path], capture_output=True, text=True)
+            assert run.returncode != 0 and "CUDA" in (run.stdout + run.stderr)
