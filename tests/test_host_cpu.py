@@ -200,3 +200,43 @@ def test_cpp_caller_example_builds_against_the_reference_headers():
         if not torch.cuda.is_available():
             run = subprocess.run([path], capture_output=True, text=True)
             assert run.returncode != 0 and "CUDA" in (run.stdout + run.stderr)
+
+
+def test_basis_count_is_host_arithmetic_and_matches_golden_and_oracle():
+    """pspace_cuda_basis_count sizes the caller's degree table without touching the device (an exact count, not the
+    reference's overflowing factorial, BasisHelper.cpp:361-367): it must equal the row counts of the golden degree
+    tables (compiled reference), of the extended oracle beyond five variables, and SURVEY.md's table of sizes."""
+    import ctypes
+    from oracle import harness as H
+    from pspace_b200 import cabi
+    from pspace_b200.workloads import mixed_params
+    L = ctypes.CDLL(cabi.LIB_PATH)
+    L.pspace_cuda_basis_count.restype = ctypes.c_int
+    L.pspace_cuda_last_error.restype = ctypes.c_char_p
+
+    def count(pmax, bt):
+        a = np.ascontiguousarray(pmax, dtype=np.intc)
+        n = ctypes.c_longlong(-1)
+        rc = L.pspace_cuda_basis_count(ctypes.c_int(len(a)), ctypes.c_void_p(a.ctypes.data), ctypes.c_int(bt), ctypes.byref(n))
+        return rc, n.value
+
+    g = load_golden("basis_degrees")
+    for idx in range(int(g["ncases"])):
+        rc, n = count(g[f"pmax_{idx}"], int(g[f"bt_{idx}"]))
+        assert rc == 0 and n == g[f"deg_{idx}"].shape[0]
+    for nv, p, bt in ((6, 2, 1), (7, 2, 0), (8, 3, 0), (10, 3, 1), (9, 1, 0), (12, 2, 1)):
+        o = H.CpuContainer(H.oracle_api(False), mixed_params(nv, p), bt).initialize_basis([p] * nv)
+        assert count([p] * nv, bt) == (0, o.N)
+    # SURVEY.md section 8 table
+    assert count([3, 3, 3], 0) == (0, 64)
+    assert count([4] * 5, 1) == (0, 126)
+    assert count([5] * 4, 0) == (0, 1296)
+    assert count([3] * 8, 0) == (0, 65536)
+    assert count([3] * 10, 1) == (0, 286)
+    # mixed caps: complete basis keeps sum <= max(pmax) with the per-variable caps still applied
+    assert count([4, 3], 1) == (0, 14)
+    # loud on bad input
+    rc, _ = count([3] * 33, 0)
+    assert rc != 0 and L.pspace_cuda_last_error()
+    rc, _ = count([3, -1], 0)
+    assert rc != 0
