@@ -67,7 +67,7 @@ int pspace_cuda_create(pspace_ctx **out, int device, int is_complex, int nvars, 
 int pspace_cuda_destroy(pspace_ctx *c) {
   if (!c) return PSPACE_OK;
   cudaSetDevice(c->device);
-  cudaFree(c->d_deg); cudaFree(c->d_zp); cudaFree(c->d_yp); cudaFree(c->d_wp); cudaFree(c->d_T);
+  cudaFree(c->d_deg); cudaFree(c->d_zp); cudaFree(c->d_yp); cudaFree(c->d_wp); cudaFree(c->d_T); cudaFree(c->d_Tw);
   cudaFree(c->d_qdig); cudaFree(c->d_W);
   cudaFree(c->panel_u.d); cudaFree(c->panel_w.d);
   cudaFree(c->d_scratch_in); cudaFree(c->d_scratch_out); cudaFree(c->d_scratch_ws);
@@ -402,6 +402,7 @@ long long pspace_cuda_launch_count(const pspace_ctx *c) { return c ? c->launches
 int pspace_cuda_set_option(pspace_ctx *c, const char *name, int value) {
   if (!c || !name) return ps_fail(PSPACE_EINVAL, "null argument");
   if (!strcmp(name, "force_generic")) { c->force_generic = value; return PSPACE_OK; }
+  if (!strcmp(name, "force_panel")) { c->force_panel = value; return PSPACE_OK; }
   if (!strcmp(name, "slab_mb")) { c->slab_bytes = (long long)value << 20; return PSPACE_OK; }
   if (!strcmp(name, "panel_cache")) { c->panel_cache = value; c->invalidate_panels(); return PSPACE_OK; }
   return ps_fail(PSPACE_EINVAL, "unknown option %s", name);

@@ -27,6 +27,7 @@ struct pspace_ctx {
   int toff[PSPACE_MAX_VARS + 1] = {0};   // table offsets (scalars): T_d at toff[d], (pmax[d]+1) x nq[d], row-major
   int tsz = 0;
   double *d_T = nullptr;
+  double *d_Tw = nullptr;                // weighted tables Tw_d[alpha][i] = T_d[alpha][i] * w_d[i]  (same offsets as d_T)
   int DP = 16;                           // bytes per row of the digit table (16 or 32)
   uint8_t *d_qdig = nullptr;             // [Q][DP] mixed-radix digits of q (last variable fastest)
   double *d_W = nullptr;                 // [Q] scalars
@@ -50,6 +51,7 @@ struct pspace_ctx {
   PanelSlot panel_u, panel_w;
   void invalidate_panels() { panel_u.valid = panel_w.valid = false; }
   int panel_cache = 1;                   // reuse a panel when the (row range, q-range) of a call repeats
+  int force_panel = 0;                   // tests / bench: one-pass operators through the round-1 panel kernels
   int force_generic = 0;                 // tests: force the cp.async kernel even where TMA is usable
   double plan_flop = 0.0;
   // scratch owned by the context for the host-buffer entry points
@@ -108,6 +110,11 @@ int ps_project(const pspace_ctx *ctx, int is_matrix, const pspace_project_args *
                void *d_ws, size_t ws_bytes, cudaStream_t st);
 int ps_project_ex(const pspace_ctx *ctx, int is_matrix, const pspace_project_args *a, const double *d_in, double *d_out,
                   void *d_ws, size_t ws_bytes, cudaStream_t st, const PeerInfo *peer);
+// factored-operand vector projection (vproject.cu)
+size_t ps_vproject_workspace(const pspace_ctx *ctx, const pspace_project_args *a);
+bool ps_vproject_usable(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_in);
+int ps_vproject(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_in, double *d_out, void *d_ws,
+                size_t ws_bytes, cudaStream_t st);
 int ps_peer_layout(const pspace_ctx *ctx, const pspace_project_args *a, int world, long long *recv_elems);
 int ps_peer_reduce_gather(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_recv, double *const *peer_out,
                           int world, int rank, cudaStream_t st);

@@ -2,14 +2,23 @@
 // caller:      U[q][c] = sum_k psi_k(z_q) V[k][c]
 // Replaces getDeterministicStates / getDeterministicAdjoint of the reference caller
 // (examples/stacs/cpp/TACSStochasticElement.cpp:53-120: for every (i,j,q) it recomputes u_q with N calls of
-// pc->basis(k,zq) per node; pspace/core.py:788-792).  Here it is one (nq x N).(N x m) FP64 GEMM per call:
-//   * left operand = the unweighted basis panel P[part][q][k] written by k_psi_panel (project.cu) — q-major,
-//     so a DMMA A-fragment row is a quadrature point and the fragment k index is the basis index;
-//   * right operand V[k][c] (N x m, row-major; complex: interleaved re/im columns), staged whole rows at a time;
-//   * DMMA.8x8x4 accumulation, 16-byte cp.async double-buffered K pipeline, conflict-free pitches (== 4 mod 16);
+// pc->basis(k,zq) per node; pspace/core.py:788-792).  Here it is one (nq x N).(N x m) FP64 GEMM per call.
+//
+// k_expand_f (default; V TMA-addressable = even real column count, 16-byte aligned): factored operand, see factored.cuh.
+//   psi_k(z_q) = P_k[q div L] * S_k[q mod L].  Persistent CTAs walk (256-point tile, column tile) pairs; the K loop runs
+//   over chunks of KC basis rows through a TMA + mbarrier ring.  Per stage the producer warps write S (KC rows x L tail
+//   points) and P (KC rows x the prefix blocks of the tile) into shared memory — products of the L1-resident 1-D tables in
+//   the reference's order within each factor — and one elected thread fetches the V rows with TMA.  Consumer warps
+//   (32 points x BN columns each): A-fragment element (row = point, k = basis row) = S * P, ONE DMUL feeding WN DMMA.8x8x4;
+//   the accumulators are stored straight to U.  Nothing of size N x Q is ever written: algorithmic bytes 8*(Q*m + N*m),
+//   2*N*m FLOP per point, bound by the FP64 tensor pipe.
+// k_expand (operands TMA cannot address, or option force_panel): the round-1 kernel that streams the unweighted basis
+//   panel written by k_psi_panel (project.cu); the q-range is walked in slabs so that the panel never exceeds 1 GiB.
 //   * complex: U = P_re*[V] + P_im*[V'] with V'[k][2c] = -V[k][2c+1], V'[k][2c+1] = V[k][2c]  (as in project.cu).
-// Bound: HBM — it streams the panel once (8*N*nq bytes, cfg5 2.4 GB) for 2*N*m FLOP per point.
 #include "ctx.h"
+#include "factored.cuh"
+#include <algorithm>
+#include <stdio.h>
 
 namespace {
 constexpr int XT = 256;          // 8 warps, each 16 quadrature rows x BN columns
@@ -151,6 +160,269 @@ template <int WN, bool CPLX> int launch_expand(const pspace_ctx *c, const Expand
   PS_LAUNCH_CHECK(c);
   return PSPACE_OK;
 }
+
+// ======================================= factored-operand kernel ===========================================
+using namespace psf;
+constexpr int XFT = 384, XNCW = 8, XNPT = 128;
+
+struct XFParams {
+  double *U;
+  const double *T;             // unweighted 1-D tables
+  const int *deg;
+  const uint8_t *qdig;
+  long long q0, q1, Qtot, tiles_q;
+  int k0, nk, ncols_d, nvars, DP, tsz;
+  int toff[PSPACE_MAX_VARS], nq[PSPACE_MAX_VARS];
+  int dsplit, L, npfx;
+  int tiles_n, nkc, stages, stage_bytes;
+  int accumulate;
+  unsigned zero;
+};
+
+template <int WM_, int WN_, bool CPLX_> struct XTile {
+  static constexpr int WM = WM_, WN = WN_;
+  static constexpr bool CPLX = CPLX_;
+  static constexpr int W = CPLX ? 2 : 1;
+  static constexpr int BQ = XNCW * WM * 8, BN = WN * 8, LDB = BN + 4;
+  static constexpr int KC = CPLX ? 64 : 128;       // basis rows per pipeline stage
+  static constexpr int KCP = KC + 4;               // == 4 (mod 16): conflict-free S reads (row g -> consecutive tail points)
+  static constexpr int TPR = XNPT / KC;            // producer threads per basis row
+  static constexpr int V_BYTES = KC * LDB * 8;
+  static_assert(LDB % 16 == 4 || LDB % 16 == 12, "V pitch");
+  __host__ __device__ static int stage_bytes(int L, int npfx) { return (V_BYTES + W * (L + npfx) * KCP * 8 + 127) / 128 * 128; }
+  __host__ __device__ static size_t eo_bytes(int nvars) { return ((size_t)TPR * nvars * KC * 2 + 15) & ~(size_t)15; }
+  __host__ __device__ static size_t tab_bytes(int tsz) { return tsz <= psf::TAB_SMEM_MAX ? (size_t)tsz * W * 8 : 0; }
+  __host__ __device__ static size_t header_bytes(int nvars, int tsz) { return (eo_bytes(nvars) + tab_bytes(tsz) + 127) / 128 * 128; }
+};
+
+template <class TL>
+__global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFParams p, const __grid_constant__ CUtensorMap tmapV) {
+  constexpr int WM = TL::WM, WN = TL::WN, W = TL::W, BQ = TL::BQ, BN = TL::BN, LDB = TL::LDB, KC = TL::KC, KCP = TL::KCP;
+  constexpr bool CPLX = TL::CPLX;
+  constexpr bool PAIRED = CPLX && (WN % 2) == 0;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned short *eo_all = reinterpret_cast<unsigned short *>(smem);                  // [TPR][nvars][KC] producer scratch
+  double *Ts = reinterpret_cast<double *>(smem + TL::eo_bytes(p.nvars));
+  unsigned char *ring = smem + TL::header_bytes(p.nvars, p.tsz);
+  const int STAGES = p.stages;
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(ring + (size_t)STAGES * p.stage_bytes);
+  unsigned long long *empty = full + STAGES;
+  const int S_OFF = TL::V_BYTES, P_OFF = TL::V_BYTES + W * p.L * KCP * 8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long ntiles = p.tiles_q * p.tiles_n;
+  const bool tab_smem = p.tsz <= TAB_SMEM_MAX;
+  if (tab_smem)
+    for (int i = tid; i < p.tsz * W; i += XFT) Ts[i] = p.T[i];
+  const double *T = tab_smem ? Ts : p.T;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1 + XNPT); mbar_init(&empty[s], XNCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= XNCW) {
+    // =========================== PRODUCERS ================================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(56));
+    const int pt = tid - XNCW * 32, r = pt % KC, sub = pt / KC;
+    unsigned short *eo = eo_all + (size_t)sub * p.nvars * KC + r;      // my own copy of the row's table offsets, stride KC
+    if (pt == 0) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmapV) : "memory");
+    int s = 0;
+    unsigned ph = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int tn = (int)(tile % p.tiles_n);
+      const long long tq = tile / p.tiles_n;
+      const long long blk0 = (p.q0 + tq * BQ) / p.L;                  // prefix block of the tile's first point
+      {
+        // digit rows of the NEXT tile's prefix blocks into L1 ahead of use (one row per thread)
+        const long long tnext = tile + gridDim.x;
+        if (tnext < ntiles && pt < p.npfx) {
+          const long long qn = ((p.q0 + (tnext / p.tiles_n) * BQ) / p.L + pt) * p.L;
+          if (qn < p.Qtot) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p.qdig + (size_t)qn * p.DP));
+        }
+      }
+      // entries of a stage: npfx prefix values then L tail values per row; the TPR threads of a row split them in halves
+      const int ne = p.npfx + p.L;
+      const int e_lo = sub * ((ne + TL::TPR - 1) / TL::TPR), e_hi = min(ne, e_lo + (ne + TL::TPR - 1) / TL::TPR);
+      for (int kc = 0; kc < p.nkc; kc++) {
+        mbar_wait(&empty[s], ph ^ 1u);
+        unsigned char *st = ring + (size_t)s * p.stage_bytes;
+        if (pt == 0) {
+          mbar_arrive_expect_tx(&full[s], TL::V_BYTES);
+          tma_load_2d(st, &tmapV, &full[s], tn * BN, kc * KC);
+        }
+        const int kr = kc * KC + r;
+        const bool valid = kr < p.nk;
+        const int k = p.k0 + kr;
+        if (valid)
+          for (int d = 0; d < p.nvars; d++)
+            eo[d * KC] = (unsigned short)(p.toff[d] + __ldg(p.deg + (size_t)k * p.nvars + d) * p.nq[d]);
+        double *Sst = reinterpret_cast<double *>(st + S_OFF), *Pst = reinterpret_cast<double *>(st + P_OFF);
+        if (e_lo < p.npfx) {
+          const int n = min(e_hi, p.npfx) - e_lo;
+          run_products<CPLX>(T, eo, KC, p.qdig, p.DP, blk0 + e_lo, n, p.L, p.Qtot, 0, p.dsplit,
+                             p.dsplit > 0 ? p.nq[p.dsplit - 1] : 1, valid, Pst + e_lo * KCP + r, KCP, p.npfx);
+        }
+        if (e_hi > p.npfx) {
+          const int t0 = max(e_lo, p.npfx) - p.npfx, n = e_hi - p.npfx - t0;
+          run_products<CPLX>(T, eo, KC, p.qdig, p.DP, t0, n, 1, p.Qtot, p.dsplit, p.nvars, p.nq[p.nvars - 1], valid,
+                             Sst + t0 * KCP + r, KCP, p.L);
+        }
+        mbar_arrive(&full[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // =========================== CONSUMERS ================================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(216));
+    const int g = lane >> 2, kl = lane & 3;
+    const unsigned sgn = (g & 1) ? 0u : 0x80000000u;
+    auto acc_pair = [&](const double (&ac)[WM][WN][2], int a, int idx, double &v0, double &v1, int &cc) {
+      if (PAIRED) { const int b2 = idx >> 1, e = idx & 1; v0 = ac[a][2 * b2][e]; v1 = ac[a][2 * b2 + (WN > 1 ? 1 : 0)][e]; cc = 16 * b2 + 4 * kl + 2 * e; }
+      else { v0 = ac[a][idx][0]; v1 = ac[a][idx][1]; cc = 8 * idx + 2 * kl; }
+    };
+    int s = 0;
+    unsigned ph = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int tn = (int)(tile % p.tiles_n);
+      const long long tq = tile / p.tiles_n;
+      const long long qt0 = p.q0 + tq * BQ, blk0 = qt0 / p.L;
+      int soff[WM], poff[WM];
+#pragma unroll
+      for (int a = 0; a < WM; a++) {
+        long long qa = qt0 + warp * (WM * 8) + a * 8 + g;
+        if (qa >= p.q1) qa = p.q1 - 1;                               // rows past the range are computed on a valid point and not stored
+        const long long b = qa / p.L;
+        soff[a] = (int)(qa - b * p.L) * KCP + kl;
+        poff[a] = (int)(b - blk0) * KCP + kl;
+      }
+      double acc[WM][WN][2];
+#pragma unroll
+      for (int a = 0; a < WM; a++)
+#pragma unroll
+        for (int b = 0; b < WN; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+      for (int kc = 0; kc < p.nkc; kc++) {
+        mbar_wait(&full[s], ph);
+        const unsigned char *st = ring + (size_t)s * p.stage_bytes;
+        const double *bs = reinterpret_cast<const double *>(st) + kl * LDB + g;
+        const double *bs2 = reinterpret_cast<const double *>(st) + kl * LDB + 2 * g;
+        const double *Sr = reinterpret_cast<const double *>(st + S_OFF), *Si = Sr + (size_t)p.L * KCP;
+        const double *Pr = reinterpret_cast<const double *>(st + P_OFF), *Pi = Pr + (size_t)p.npfx * KCP;
+        const int ksteps = (min(KC, p.nk - kc * KC) + 3) >> 2;
+        int depi = 0;
+#pragma unroll 4
+        for (int ks = 0; ks < ksteps; ks++) {
+          double are[WM], aim[WM];
+#pragma unroll
+          for (int a = 0; a < WM; a++) {
+            const double sr = Sr[soff[a] + ks * 4], pr = Pr[poff[a] + ks * 4];
+            if (!CPLX) are[a] = sr * pr;
+            else {
+              const double si = Si[soff[a] + ks * 4], pi = Pi[poff[a] + ks * 4];
+              are[a] = sr * pr - si * pi;
+              aim[a] = sr * pi + si * pr;
+            }
+          }
+          double bfr[WN], bsw[WN];
+          if (PAIRED) {
+#pragma unroll
+            for (int b2 = 0; b2 < WN / 2; b2++) {
+              const double2 v = *reinterpret_cast<const double2 *>(bs2 + ks * 4 * LDB + 16 * b2);
+              bfr[2 * b2] = v.x; bfr[2 * b2 + 1] = v.y;
+              if (CPLX) { bsw[2 * b2] = flip_sign(v.y, 0x80000000u); bsw[2 * b2 + 1] = v.x; }
+            }
+          } else {
+#pragma unroll
+            for (int b = 0; b < WN; b++) {
+              bfr[b] = bs[ks * 4 * LDB + b * 8];
+              if (CPLX) bsw[b] = flip_sign(bs[ks * 4 * LDB + b * 8 + ((g & 1) ? -1 : 1)], sgn);
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < WM; a++)
+#pragma unroll
+            for (int b = 0; b < WN; b++) {
+              dmma884(acc[a][b][0], acc[a][b][1], are[a], bfr[b]);
+              if (CPLX) dmma884(acc[a][b][0], acc[a][b][1], aim[a], bsw[b]);
+            }
+          depi = __double2loint(are[WM - 1]) ^ __double2loint(bfr[WN - 1]);
+        }
+        // release the stage: the arrive's address depends on the last fragment registers read from it
+        const unsigned dep = (unsigned)depi & p.zero;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s], dep);
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+
+#pragma unroll
+      for (int a = 0; a < WM; a++) {
+        const long long qrel = tq * BQ + warp * (WM * 8) + a * 8 + g;
+        if (p.q0 + qrel >= p.q1) continue;
+#pragma unroll
+        for (int b = 0; b < WN; b++) {
+          double v0, v1; int cc;
+          acc_pair(acc, a, b, v0, v1, cc);
+          const int col = tn * BN + cc;
+          double *dst = p.U + (size_t)qrel * p.ncols_d + col;
+          if (col + 1 < p.ncols_d && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
+            if (p.accumulate) { const double2 o = *reinterpret_cast<double2 *>(dst); v0 += o.x; v1 += o.y; }
+            *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
+          } else {
+            if (col < p.ncols_d) dst[0] = p.accumulate ? dst[0] + v0 : v0;
+            if (col + 1 < p.ncols_d) dst[1] = p.accumulate ? dst[1] + v1 : v1;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <class TL> int launch_expand_f(const pspace_ctx *c, XFParams &p, const double *d_V, cudaStream_t st) {
+  // tail length: the candidate (product of trailing rule sizes) with the fewest table products per stage,
+  // (prefix blocks of a tile) * dsplit + L * (nvars - dsplit), that leaves room for >= 2 stages
+  const size_t head = TL::header_bytes(c->nvars, c->tsz), avail = (size_t)227 * 1024 - head - 1024 - 256;
+  int best_ds = -1, best_L = 1, best_npfx = 0;
+  double best_cost = 0;
+  long long L = 1;
+  for (int ds = c->nvars; ds >= 0; ds--) {
+    if (ds < c->nvars) L *= c->nq[ds];
+    if (L > 4096) break;
+    const int npfx = (int)((TL::BQ + L - 2) / L) + 1;
+    if ((size_t)TL::stage_bytes((int)L, npfx) * 2 > avail) continue;
+    const double cost = (double)npfx * ds + (double)L * (c->nvars - ds);
+    if (best_ds < 0 || cost < best_cost) { best_ds = ds; best_L = (int)L; best_npfx = npfx; best_cost = cost; }
+  }
+  if (best_ds < 0) return ps_fail(PSPACE_EINVAL, "evaluate_expansion: no factorisation fits shared memory");
+  p.dsplit = best_ds; p.L = best_L; p.npfx = best_npfx;
+  p.stage_bytes = TL::stage_bytes(p.L, p.npfx);
+  p.stages = (int)std::max<size_t>(2, std::min<size_t>(6, avail / p.stage_bytes));
+  const size_t smem = head + (size_t)p.stages * p.stage_bytes + 2 * p.stages * 8 + 1024;
+  p.tiles_q = (p.q1 - p.q0 + TL::BQ - 1) / TL::BQ;
+  p.tiles_n = (p.ncols_d + TL::BN - 1) / TL::BN;
+  p.nkc = (p.nk + TL::KC - 1) / TL::KC;
+  CUtensorMap tmV;
+  {
+    unsigned long long dims[2] = {(unsigned long long)p.ncols_d, (unsigned long long)p.nk};
+    unsigned long long str[1] = {(unsigned long long)p.ncols_d * 8};
+    unsigned box[2] = {(unsigned)TL::LDB, (unsigned)TL::KC};
+    int rc = ps_make_tmap(&tmV, d_V, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+  const int grid = (int)std::max<long long>(1, std::min<long long>(nsm, p.tiles_q * p.tiles_n));
+  PS_CUDA(cudaFuncSetAttribute(k_expand_f<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  k_expand_f<TL><<<grid, XFT, smem, st>>>(p, tmV);
+  PS_LAUNCH_CHECK(c);
+  pspace_ctx *mc = const_cast<pspace_ctx *>(c);
+  char buf[256];
+  snprintf(buf, sizeof buf, "%sexpand %dx%d factored operand: tail=%d vars (L=%d) prefix slots=%d KC=%d stages=%d ctas=%d", TL::CPLX ? "z " : "",
+           TL::BQ, TL::BN, c->nvars - p.dsplit, p.L, p.npfx, TL::KC, p.stages, grid);
+  mc->plan = buf;
+  mc->plan_flop = 2.0 * (double)p.nk * (double)p.ncols_d * (double)(p.q1 - p.q0) * (TL::CPLX ? 2.0 : 1.0);
+  return PSPACE_OK;
+}
 }  // namespace
 
 int ps_build_panel_rows(pspace_ctx *c, int r0, int nr, long long q0, long long q1, int weighted, double **d_panel,
@@ -166,29 +438,60 @@ int ps_expand(const pspace_ctx *c, int k0, int k1, long long q0, long long q1, i
     if (!accumulate) PS_CUDA(cudaMemsetAsync(d_U, 0, sizeof(double) * (size_t)(q1 - q0) * ncols_d, st));
     return PSPACE_OK;
   }
-  double *panel = nullptr;
-  int np = 0;
-  int rc = ps_build_panel_rows(const_cast<pspace_ctx *>(c), k0, k1 - k0, q0, q1, 0, &panel, &np, st);
-  if (rc) return rc;
-  ExpandParams p;
-  p.P = panel; p.V = d_V; p.U = d_U; p.nq = q1 - q0; p.np = np; p.nk = k1 - k0; p.ncols_d = ncols_d;
-  p.accumulate = accumulate;
-  p.vecV = (ncols_d % 2 == 0 && (reinterpret_cast<size_t>(d_V) % 16) == 0) ? 1 : 0;
   const bool z = c->is_complex;
-  // warp tile width WN*8 columns: fewest column tiles first (every column tile streams the panel again), then the
-  // fewest padded columns
+  const bool tma_ok = (ncols_d % 2) == 0 && (reinterpret_cast<size_t>(d_V) % 16) == 0;
+  if (tma_ok && !c->force_panel && !c->force_generic && c->tsz + PSPACE_MAX_NQ < 65536) {
+    XFParams f;
+    f.U = d_U; f.T = c->d_T; f.deg = c->d_deg; f.qdig = c->d_qdig;
+    f.q0 = q0; f.q1 = q1; f.Qtot = c->Q;
+    f.k0 = k0; f.nk = k1 - k0; f.ncols_d = ncols_d; f.nvars = c->nvars; f.DP = c->DP; f.tsz = c->tsz;
+    for (int d = 0; d < PSPACE_MAX_VARS; d++) { f.toff[d] = d < c->nvars ? c->toff[d] : 0; f.nq[d] = d < c->nvars ? c->nq[d] : 1; }
+    f.accumulate = accumulate; f.zero = 0;
+    // column tile: fewest tiles first (each regenerates the operand), then the fewest padded columns
+    static const int cand[] = {6, 4, 3, 2, 1};
+    const int min_tiles = (ncols_d + 47) / 48;
+    int wn = 6;
+    for (int k = 0; k < 5; k++)
+      if ((ncols_d + cand[k] * 8 - 1) / (cand[k] * 8) == min_tiles) wn = cand[k];
+    if (z && wn == 3) wn = 4;       // complex tiles hold whole (re,im) pairs: even WN
+    if (z && wn == 1) wn = 2;
+    switch (wn) {
+      case 6: return z ? launch_expand_f<XTile<4, 6, true>>(c, f, d_V, st) : launch_expand_f<XTile<4, 6, false>>(c, f, d_V, st);
+      case 4: return z ? launch_expand_f<XTile<4, 4, true>>(c, f, d_V, st) : launch_expand_f<XTile<4, 4, false>>(c, f, d_V, st);
+      case 3: return launch_expand_f<XTile<4, 3, false>>(c, f, d_V, st);
+      case 2: return z ? launch_expand_f<XTile<4, 2, true>>(c, f, d_V, st) : launch_expand_f<XTile<4, 2, false>>(c, f, d_V, st);
+      default: return launch_expand_f<XTile<4, 1, false>>(c, f, d_V, st);
+    }
+  }
+  // panel path, in q-slabs of at most 1 GiB of panel
+  const long long np_est = ((k1 - k0) + 1) & ~1;
+  long long slab = ((1LL << 30) / ((long long)c->width * np_est * 8)) / XBM * XBM;
+  if (slab < XBM) slab = XBM;
   static const int cand[] = {8, 6, 4, 3, 2, 1};
   const int min_tiles = (ncols_d + 63) / 64;
   int wn = 8;
   for (int k = 0; k < 6; k++)
     if ((ncols_d + cand[k] * 8 - 1) / (cand[k] * 8) == min_tiles) wn = cand[k];
-  switch (wn) {
-    case 8: rc = z ? launch_expand<8, true>(c, p, st) : launch_expand<8, false>(c, p, st); break;
-    case 6: rc = z ? launch_expand<6, true>(c, p, st) : launch_expand<6, false>(c, p, st); break;
-    case 4: rc = z ? launch_expand<4, true>(c, p, st) : launch_expand<4, false>(c, p, st); break;
-    case 3: rc = z ? launch_expand<3, true>(c, p, st) : launch_expand<3, false>(c, p, st); break;
-    case 2: rc = z ? launch_expand<2, true>(c, p, st) : launch_expand<2, false>(c, p, st); break;
-    default: rc = z ? launch_expand<1, true>(c, p, st) : launch_expand<1, false>(c, p, st); break;
+  int rc = PSPACE_OK;
+  for (long long qs = q0; qs < q1 && rc == PSPACE_OK; qs += slab) {
+    const long long qe = std::min(q1, qs + slab);
+    double *panel = nullptr;
+    int np = 0;
+    rc = ps_build_panel_rows(const_cast<pspace_ctx *>(c), k0, k1 - k0, qs, qe, 0, &panel, &np, st);
+    if (rc) return rc;
+    ExpandParams p;
+    p.P = panel; p.V = d_V; p.U = d_U + (size_t)(qs - q0) * ncols_d; p.nq = qe - qs; p.np = np; p.nk = k1 - k0; p.ncols_d = ncols_d;
+    p.accumulate = accumulate;
+    p.vecV = tma_ok ? 1 : 0;
+    switch (wn) {
+      case 8: rc = z ? launch_expand<8, true>(c, p, st) : launch_expand<8, false>(c, p, st); break;
+      case 6: rc = z ? launch_expand<6, true>(c, p, st) : launch_expand<6, false>(c, p, st); break;
+      case 4: rc = z ? launch_expand<4, true>(c, p, st) : launch_expand<4, false>(c, p, st); break;
+      case 3: rc = z ? launch_expand<3, true>(c, p, st) : launch_expand<3, false>(c, p, st); break;
+      case 2: rc = z ? launch_expand<2, true>(c, p, st) : launch_expand<2, false>(c, p, st); break;
+      default: rc = z ? launch_expand<1, true>(c, p, st) : launch_expand<1, false>(c, p, st); break;
+    }
   }
+  const_cast<pspace_ctx *>(c)->plan = "expand: basis panel streamed (round-1 kernel)";
   return rc;
 }

@@ -27,6 +27,7 @@
 //   the q-range is cut into `ksplit` slices over blockIdx.y whose partial windows k_reduce_slices adds in slice order.
 #include "ctx.h"
 #include <algorithm>
+#include <atomic>
 #include <cuda.h>
 #include <stdio.h>
 
@@ -939,17 +940,17 @@ __global__ void __launch_bounds__(256) k_peer_reduce_gather(const __grid_constan
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn resolve_encode_tiled() {
+  void *sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+  return (EncodeTiledFn)sym;
+}
 int make_tmap(CUtensorMap *tm, const double *base, int rank, const unsigned long long *dims,
               const unsigned long long *strides_bytes /*rank-1*/, const unsigned *box) {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void *sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym)
-      return ps_fail(PSPACE_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
-    fn = (EncodeTiledFn)sym;
-  }
+  static const EncodeTiledFn fn = resolve_encode_tiled();     // C++11 magic static: initialised once, thread-safe
+  if (!fn) return ps_fail(PSPACE_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t gdim[3], gstr[2];
   cuuint32_t bx[3], estr[3] = {1, 1, 1};
   for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; }
@@ -992,13 +993,12 @@ int ensure_panel(pspace_ctx *c, bool weighted, int r0, int nr, long long q0, lon
   const size_t smem = (size_t)(((c->tsz * W + 1) & ~1) + PSI_PTS * W) * 8 + (size_t)PSI_PTS * c->DP;
   const int nt = std::min(PSI_MAXT, (pp.nr_pad + 31) & ~31);
   const dim3 grid((unsigned)((nq + PSI_PTS - 1) / PSI_PTS), (unsigned)((pp.nr_pad + nt - 1) / nt));
-  if (c->is_complex) {
-    PS_CUDA(cudaFuncSetAttribute(k_psi_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_psi_panel<true><<<grid, nt, smem, st>>>(pp);
-  } else {
-    PS_CUDA(cudaFuncSetAttribute(k_psi_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_psi_panel<false><<<grid, nt, smem, st>>>(pp);
+  if (smem > 48 * 1024) {   // only then is an opt-in needed (tables of more than ~5000 entries); never on the BASELINE configs
+    if (c->is_complex) PS_CUDA(cudaFuncSetAttribute(k_psi_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else PS_CUDA(cudaFuncSetAttribute(k_psi_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
+  if (c->is_complex) k_psi_panel<true><<<grid, nt, smem, st>>>(pp);
+  else k_psi_panel<false><<<grid, nt, smem, st>>>(pp);
   PS_LAUNCH_CHECK(c);
   s.r0 = r0; s.nr = nr; s.q0 = q0; s.q1 = q1;
   s.valid = true;
@@ -1078,15 +1078,15 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
       unsigned box[3] = {(unsigned)TL::BIP, (unsigned)LY::KQW, (unsigned)TL::W};
       if ((rc = make_tmap(&tmI, d_pi, 3, dims, str, box))) return rc;
     } else tmI = tmJ;
-    static bool attr_ws_dev[64] = {false};   // per instantiation and device (function attributes are per device)
-    bool &attr_ws = attr_ws_dev[c->device & 63];
-    if (!attr_ws) {
+    static std::atomic<bool> attr_ws_dev[64];   // per instantiation and device (function attributes are per device);
+    std::atomic<bool> &attr_ws = attr_ws_dev[c->device & 63];   // setting an attribute twice is harmless, the flag is atomic
+    if (!attr_ws.load(std::memory_order_acquire)) {
       PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       if (MAT) {
         PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, MAT ? EPI_MASKED : EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, MAT ? EPI_PEER : EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       }
-      attr_ws = true;
+      attr_ws.store(true, std::memory_order_release);
     }
     p.out = d_out;
     p.accumulate = a->accumulate;
@@ -1122,11 +1122,11 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
   }
   size_t smem = TL::smem_bytes(c->tsz, c->nvars);
   if (smem > 227 * 1024) return ps_fail(PSPACE_EINVAL, "1-D tables too large for the staged kernel (%zu B shared memory)", smem);
-  static bool attr_set_dev[64] = {false};   // per instantiation and device
-  bool &attr_set = attr_set_dev[c->device & 63];
-  if (!attr_set) {
+  static std::atomic<bool> attr_set_dev[64];   // per instantiation and device
+  std::atomic<bool> &attr_set = attr_set_dev[c->device & 63];
+  if (!attr_set.load(std::memory_order_acquire)) {
     PS_CUDA(cudaFuncSetAttribute(k_project<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_set.store(true, std::memory_order_release);
   }
   const bool split = pl.ksplit > 1;
   p.out = split ? (double *)d_ws : d_out;
@@ -1179,11 +1179,11 @@ const Variant VEC_VARIANTS[] = {{1, V32::BM, V32::BN, 0, V32::BM, 1, "dmma vec 1
                                 {3, V24::BM, V24::BN, 0, V24::BM, 1, "dmma vec 128x24"}};
 
 int sm_count(int device) {
-  static int cached[64] = {0};
-  if (device < 64 && cached[device]) return cached[device];
+  static std::atomic<int> cached[64];
+  if (device < 64) { const int v = cached[device].load(std::memory_order_relaxed); if (v) return v; }
   int n = 148;
   cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
-  if (device < 64) cached[device] = n;
+  if (device < 64) cached[device].store(n, std::memory_order_relaxed);
   return n;
 }
 
@@ -1255,6 +1255,11 @@ int make_plan(const pspace_ctx *c, int is_matrix, const pspace_project_args *a, 
 }
 }  // namespace
 
+int ps_make_tmap(CUtensorMap *tm, const double *base, int rank, const unsigned long long *dims,
+                 const unsigned long long *strides_bytes, const unsigned *box) {
+  return make_tmap(tm, base, rank, dims, strides_bytes, box);
+}
+
 // Unweighted / weighted basis panel of rows [r0, r0+nr) over [q0,q1) in the context's panel slot (used by expand.cu)
 int ps_build_panel_rows(pspace_ctx *c, int r0, int nr, long long q0, long long q1, int weighted, double **d_panel,
                         int *nr_pad, cudaStream_t st) {
@@ -1263,6 +1268,14 @@ int ps_build_panel_rows(pspace_ctx *c, int r0, int nr, long long q0, long long q
 
 size_t ps_project_workspace(const pspace_ctx *c, int is_matrix, const pspace_project_args *a) {
   Plan pl;
+  if (!is_matrix) {
+    // which vector kernel runs depends on the operand's alignment, known only at the call — size for either
+    // (`variant` ids above 3 name tiles of the factored-operand kernel only)
+    pspace_project_args b = *a;
+    if (b.variant > 3) b.variant = 0;
+    const size_t w_old = make_plan(c, 0, &b, pl) == PSPACE_OK ? pl.ws_bytes : 0;
+    return std::max(w_old, ps_vproject_workspace(c, a));
+  }
   if (make_plan(c, is_matrix, a, pl) != PSPACE_OK) return 0;
   return pl.ws_bytes;
 }
@@ -1312,7 +1325,11 @@ int ps_peer_reduce_gather(const pspace_ctx *c, const pspace_project_args *a, con
 int ps_project_ex(const pspace_ctx *c, int is_matrix, const pspace_project_args *a, const double *d_in, double *d_out,
                   void *d_ws, size_t ws_bytes, cudaStream_t st, const PeerInfo *peer) {
   Plan pl;
-  int rc = make_plan(c, is_matrix, a, pl);
+  // vector mode: `variant` may name a tile of the factored-operand kernel (ids 1..8), which make_plan does not know
+  const bool to_vf = !is_matrix && !peer && ps_vproject_usable(c, a, d_in);
+  pspace_project_args a_chk = *a;
+  if (to_vf) a_chk.variant = 0;
+  int rc = make_plan(c, is_matrix, &a_chk, pl);
   if (rc) return rc;
   pspace_ctx *mc = const_cast<pspace_ctx *>(c);
   const int ncols_d = a->ncols * c->width;
@@ -1322,6 +1339,9 @@ int ps_project_ex(const pspace_ctx *c, int is_matrix, const pspace_project_args 
     if (!a->accumulate) PS_CUDA(cudaMemsetAsync(d_out, 0, pl.out_elems * sizeof(double), st));
     return PSPACE_OK;
   }
+  // vector projection: the factored-operand kernel (vproject.cu) takes every TMA-addressable call; the kernels below
+  // remain for odd column counts / unaligned operands (generic, in-kernel psi) and as the measured round-1 alternative
+  if (to_vf) return ps_vproject(c, a, d_in, d_out, d_ws, ws_bytes, st);
   if (pl.ws_bytes > ws_bytes || (pl.ws_bytes && !d_ws))
     return ps_fail(PSPACE_EINVAL, "workspace of %zu bytes needed, %zu given", pl.ws_bytes, ws_bytes);
 

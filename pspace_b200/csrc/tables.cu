@@ -33,10 +33,10 @@ __device__ __forceinline__ void raw_rule(int kind, int n, int i, double &x, doub
 
 // one block per parameter: rule (z,y,w)[nq] then T[alpha][iq] = unit_poly(z_iq, alpha), alpha <= pmax
 template <typename S>
-__global__ void k_rules_tables(TabParams p, double *zp, double *yp, double *wp, double *T, int with_tables) {
+__global__ void k_rules_tables(TabParams p, double *zp, double *yp, double *wp, double *T, double *Tw, int with_tables) {
   typedef scalar_of<S> SO;
   const int d = blockIdx.x, n = p.nq[d], kind = p.kinds[d];
-  __shared__ double zs[2 * PSPACE_MAX_NQ];
+  __shared__ double zs[2 * PSPACE_MAX_NQ], ws[2 * PSPACE_MAX_NQ];
   S a = SO::load(p.p1, d), b = SO::load(p.p2, d);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double x, w;
@@ -47,6 +47,7 @@ __global__ void k_rules_tables(TabParams p, double *zp, double *yp, double *wp, 
     SO::store(yp, p.roff[d] + i, y);
     SO::store(wp, p.roff[d] + i, wo);
     SO::store(zs, i, z);
+    SO::store(ws, i, wo);
   }
   __syncthreads();
   if (!with_tables) return;
@@ -55,6 +56,8 @@ __global__ void k_rules_tables(TabParams p, double *zp, double *yp, double *wp, 
     int alpha = e / n, i = e % n;
     S v = ps_param_basis<S>(kind, SO::load(zs, i), alpha);
     SO::store(T, p.toff[d] + alpha * n + i, v);
+    // weighted table for the factored one-pass kernels: prod_d Tw_d = w_q psi_k(z_q) up to rounding order
+    SO::store(Tw, p.toff[d] + alpha * n + i, s_mul(v, SO::load(ws, i)));
   }
 }
 
@@ -237,15 +240,16 @@ int ps_build_tables(pspace_ctx *c, cudaStream_t st) {
     c->cap_rules = need_rules;
   }
   if (with_tables && need_T > c->cap_T) {
-    if (c->d_T) { PS_CUDA(cudaFree(c->d_T)); c->d_T = nullptr; }
+    if (c->d_T) { PS_CUDA(cudaFree(c->d_T)); PS_CUDA(cudaFree(c->d_Tw)); c->d_T = c->d_Tw = nullptr; }
     c->cap_T = 0;
     PS_CUDA(cudaMalloc(&c->d_T, need_T));
+    PS_CUDA(cudaMalloc(&c->d_Tw, need_T));
     c->cap_T = need_T;
   }
   TabParams p;
   fill_tab(c, p);
-  if (c->is_complex) k_rules_tables<cplx><<<c->nvars, 128, 0, st>>>(p, c->d_zp, c->d_yp, c->d_wp, c->d_T, with_tables);
-  else k_rules_tables<double><<<c->nvars, 128, 0, st>>>(p, c->d_zp, c->d_yp, c->d_wp, c->d_T, with_tables);
+  if (c->is_complex) k_rules_tables<cplx><<<c->nvars, 128, 0, st>>>(p, c->d_zp, c->d_yp, c->d_wp, c->d_T, c->d_Tw, with_tables);
+  else k_rules_tables<double><<<c->nvars, 128, 0, st>>>(p, c->d_zp, c->d_yp, c->d_wp, c->d_T, c->d_Tw, with_tables);
   PS_LAUNCH_CHECK(c);
   c->tables_ready = with_tables;
   return PSPACE_OK;

@@ -1,0 +1,542 @@
+// (3a) Vector (residual-type) Galerkin projection, factored-operand kernel.
+//
+//      F[k][c] = sum_q (w_q psi_k(z_q)) f[q][c]                      TACSStochasticElement.cpp:283-311 (addResidual),
+//                                                                    :196-238 (getInitConditions), :487-530 (evalPointQuantity)
+//
+// the dense (N x Q).(Q x m) contraction with a GENERATED left operand, one pass over f.  Round 1 wrote the weighted
+// operand to HBM first (k_psi_panel: 2.4 GB for cfg5, 68.7 GB for cfg4) and streamed it back once — 25x the algorithmic
+// traffic and HBM-bound at 0.31 of the FP64 peak.  Here the operand never leaves the SM (see factored.cuh):
+//
+//   w_q psi_k(z_q) = P_k[q div L] * S_k[q mod L]     with the weighted 1-D tables Tw_d = w_d T_d
+//
+//   * S (rows of the CTA's row tile x L tail points) is written to shared memory once per work segment by the producer
+//     warps; P (rows x the <= npfx prefix blocks a 64-point stage touches) once per stage, next to the f tile that one
+//     elected producer thread fetches with TMA (cp.async.bulk.tensor, mbarrier expect_tx, zero-filled ragged edges);
+//   * consumer warps: A-fragment element = S * P (ONE DMUL, two shared-memory reads), feeding WN DMMA.8x8x4 each;
+//   * warp grid RG row groups x KG k-groups: with KG = 2 the two warps of an SM sub-partition take alternate stages
+//     (their chunk boundaries interleave by construction) and add their accumulators through shared memory at the end
+//     of a segment — this is what makes a 96-row tile possible (286 basis rows = 3 x 96 - 2, instead of 3 x 128 - 98);
+//   * work = (row tile, column tile, 64-point chunk) units cut into G equal contiguous ranges (stream-K, one persistent
+//     CTA per SM): full tiles are stored straight to F, partial ones go to a workspace and k_vfixup adds the pieces of
+//     each tile in CTA order (deterministic, no atomics);
+//   * a stage is released with an mbarrier arrive whose address depends on the stage's last fragment registers.
+//
+// Algorithmic work: 2*m FLOP per (q,k) (x4 complex), bytes 8*(Q*m + N*m).  Bound: FP64 tensor pipe (DMMA); the operand
+// generation adds 1 DMUL per m/8.. DMMAs on the shared FP64 datapath (about 4 % for m = 24).
+#include "ctx.h"
+#include "factored.cuh"
+#include <algorithm>
+#include <stdio.h>
+
+namespace {
+using namespace psf;
+
+constexpr int VT = 384;        // 8 consumer warps + 4 producer warps
+constexpr int VNCW = 8, VNPT = 128;
+constexpr int VKQ = 64;        // quadrature points per pipeline stage
+
+struct VParams {
+  double *out;                 // F rows [nk][ncols_d]
+  double *sk_ws;               // stream-K partial tiles [G][2][BM*BN]
+  const double *Tw;            // weighted 1-D tables
+  const int *deg;
+  const uint8_t *qdig;
+  long long q0, q1, Qtot;
+  int k0, nk, ncols_d, nvars, DP, tsz;
+  int toff[PSPACE_MAX_VARS], nq[PSPACE_MAX_VARS];
+  int dsplit, L, npfx;         // tail = variables [dsplit, nvars); L = prod of their rule sizes; prefix slots per stage
+  int tiles_r, tiles_n, nchunk;
+  int stages, stage_bytes;     // pipeline ring (host-sized)
+  int accumulate;
+  unsigned zero;               // run-time 0 (stage-release dependency, see mbar_arrive)
+};
+
+template <int WM_, int WN_, int RG_, int KG_, bool CPLX_> struct VTile {
+  static constexpr int WM = WM_, WN = WN_, RG = RG_, KG = KG_;
+  static constexpr bool CPLX = CPLX_;
+  static constexpr int W = CPLX ? 2 : 1;
+  static constexpr int BM = RG * WM * 8, BN = WN * 8;
+  static constexpr int LDB = BN + 4;          // == 4 or 12 (mod 16): conflict-free B fragments
+  static constexpr int SP = BM + 4;           // == 4 (mod 16): conflict-free S reads (k = lane%4 -> consecutive tail points)
+  static constexpr int B_BYTES = VKQ * LDB * 8;
+  static_assert(RG * KG == VNCW, "8 consumer warps");
+  static_assert(LDB % 16 == 4 || LDB % 16 == 12, "B pitch");
+  // fixed shared-memory header: S planes, row offsets, accumulator exchange
+  __host__ __device__ static size_t s_bytes(int L) { return (size_t)W * L * SP * 8; }
+  __host__ __device__ static size_t eo_bytes(int nvars) { return ((size_t)nvars * BM * 2 + 15) & ~(size_t)15; }
+  __host__ __device__ static size_t xchg_bytes() { return KG == 2 ? (size_t)RG * 32 * WM * WN * 2 * 8 : 0; }
+  __host__ __device__ static int stage_bytes(int npfx) { return (B_BYTES + W * npfx * SP * 8 + VKQ * 8 + 127) / 128 * 128; }
+  __host__ __device__ static size_t tab_bytes(int tsz) { return tsz <= psf::TAB_SMEM_MAX ? (size_t)tsz * W * 8 : 0; }
+  __host__ __device__ static size_t header_bytes(int L, int nvars, int tsz) {
+    return (s_bytes(L) + eo_bytes(nvars) + xchg_bytes() + tab_bytes(tsz) + 127) / 128 * 128;
+  }
+};
+
+// stream-K decomposition shared by the kernel and the fix-up: CTA g owns whole tiles g, g+G, ... of the first
+// floor(ntiles/G) waves and the contiguous range [r0,r1) of the remaining rem_tiles*nchunk (tile, chunk) units
+struct SkWork {
+  int G, nchunk, ntiles, nfull;
+  long long rem_units;
+  __host__ __device__ SkWork(int G_, int ntiles_, int nchunk_) : G(G_), nchunk(nchunk_), ntiles(ntiles_) {
+    nfull = ntiles / G;
+    rem_units = (long long)(ntiles - nfull * G) * nchunk;
+  }
+  __host__ __device__ long long lo(int g) const { return rem_units * g / G; }
+  __host__ __device__ int nseg(int g) const {
+    const long long r0 = lo(g), r1 = lo(g + 1);
+    return nfull + (r1 > r0 ? 1 : 0) + ((r1 > r0 && r1 > (r0 / nchunk + 1) * (long long)nchunk) ? 1 : 0);
+  }
+  __host__ __device__ void segment(int g, int sidx, int &tile, int &c0, int &c1, int &slot) const {
+    if (sidx < nfull) { tile = sidx * G + g; c0 = 0; c1 = nchunk; slot = -1; return; }
+    const long long r0 = lo(g), r1 = lo(g + 1), ta = r0 / nchunk;
+    if (sidx == nfull) {
+      tile = nfull * G + (int)ta; c0 = (int)(r0 - ta * nchunk);
+      c1 = (int)(r1 - ta * nchunk < nchunk ? r1 - ta * nchunk : nchunk); slot = 0;
+    } else { tile = nfull * G + (int)ta + 1; c0 = 0; c1 = (int)(r1 - (ta + 1) * nchunk); slot = 1; }
+  }
+};
+
+template <class TL>
+__global__ void __launch_bounds__(VT, 1) k_project_vf(const __grid_constant__ VParams p, const __grid_constant__ CUtensorMap tmapB) {
+  constexpr int WM = TL::WM, WN = TL::WN, RG = TL::RG, KG = TL::KG, W = TL::W, BM = TL::BM, BN = TL::BN;
+  constexpr int LDB = TL::LDB, SP = TL::SP;
+  constexpr bool CPLX = TL::CPLX;
+  constexpr bool PAIRED = CPLX && (WN % 2) == 0;
+
+  extern __shared__ __align__(1024) unsigned char smem[];
+  double *S = reinterpret_cast<double *>(smem);                                             // [W][L][SP]
+  unsigned short *eo = reinterpret_cast<unsigned short *>(smem + TL::s_bytes(p.L));         // [nvars][BM]
+  double *xchg = reinterpret_cast<double *>(smem + TL::s_bytes(p.L) + TL::eo_bytes(p.nvars));
+  double *Ts = reinterpret_cast<double *>(smem + TL::s_bytes(p.L) + TL::eo_bytes(p.nvars) + TL::xchg_bytes());
+  unsigned char *ring = smem + TL::header_bytes(p.L, p.nvars, p.tsz);
+  const int STAGES = p.stages;
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(ring + (size_t)STAGES * p.stage_bytes);
+  unsigned long long *empty = full + STAGES;
+  unsigned long long *s_full = empty + STAGES, *s_free = s_full + 1;
+  const int P_OFF = TL::B_BYTES, IDX_OFF = TL::B_BYTES + W * p.npfx * SP * 8;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const SkWork wk(gridDim.x, p.tiles_r * p.tiles_n, p.nchunk);
+  const int gcta = blockIdx.x, nseg = wk.nseg(gcta);
+
+  const bool tab_smem = p.tsz <= TAB_SMEM_MAX;
+  if (tab_smem)
+    for (int i = tid; i < p.tsz * W; i += VT) Ts[i] = p.Tw[i];
+  const double *T = tab_smem ? Ts : p.Tw;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1 + VNPT); mbar_init(&empty[s], RG); }
+    mbar_init(s_full, VNPT);
+    mbar_init(s_free, VNCW);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= VNCW) {
+    // =========================== PRODUCERS: TMA + the factor tables =====================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(56));
+    const int pt = tid - VNCW * 32;                  // 0..127 = row of the tile
+    if (pt == 0) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmapB) : "memory");
+    int s = 0;
+    unsigned ph = 0;
+    for (int sidx = 0; sidx < nseg; sidx++) {
+      int tile, c0, c1, slot;
+      wk.segment(gcta, sidx, tile, c0, c1, slot);
+      const int tn = tile % p.tiles_n, tr = tile / p.tiles_n;
+      const int k = p.k0 + tr * BM + pt;
+      const bool valid = pt < BM && k < p.k0 + p.nk;
+      // ---- per-segment: row offsets and the tail table S of this row tile ----
+      if (sidx > 0) mbar_wait(s_free, (unsigned)(sidx - 1) & 1u);
+      if (pt < BM) {
+        for (int d = 0; d < p.nvars; d++)
+          eo[d * BM + pt] = (unsigned short)(valid ? p.toff[d] + __ldg(p.deg + (size_t)k * p.nvars + d) * p.nq[d] : 0);
+        run_products<CPLX>(T, eo + pt, BM, p.qdig, p.DP, 0, p.L, 1, p.Qtot, p.dsplit, p.nvars, p.nq[p.nvars - 1], valid, S + pt, SP, p.L);
+      }
+      mbar_arrive(s_full);
+      // ---- per stage: f tile by TMA, prefix values P, point -> (tail index, prefix slot) map ----
+      // prefix block of the stage's first point = hi*nql + lo (lo = digit of the last prefix variable); the product over
+      // the other prefix variables is cached per hi — it changes once every nql*L points
+      const int nql = p.dsplit > 0 ? p.nq[p.dsplit - 1] : 1;
+      const int eo_last = p.dsplit > 0 ? (int)eo[(p.dsplit - 1) * BM + (pt < BM ? pt : 0)] : 0;
+      const long long blk0 = (p.q0 + (long long)c0 * VKQ) / p.L;
+      int rem = (int)((p.q0 + (long long)c0 * VKQ) - blk0 * p.L);
+      long long hi = blk0 / nql;
+      int lo = (int)(blk0 - hi * nql);
+      long long c_hi = -1;
+      double cbr = 1.0, cbi = 0.0;
+      for (int c = c0; c < c1; c++) {
+        mbar_wait(&empty[s], ph ^ 1u);
+        unsigned char *st = ring + (size_t)s * p.stage_bytes;
+        if (pt == 0) {
+          mbar_arrive_expect_tx(&full[s], TL::B_BYTES);
+          tma_load_2d(st, &tmapB, &full[s], tn * BN, c * VKQ);
+        }
+        double *Pst = reinterpret_cast<double *>(st + P_OFF);
+        if (pt < BM) {
+          for (int pb = 0; pb < p.npfx; pb++) {
+            int l = lo + pb;
+            long long h = hi;
+            while (l >= nql) { l -= nql; h++; }
+            const long long qb = (h * nql + l) * p.L;                       // first point of the block
+            double vr = 0.0, vi = 0.0;
+            if (valid && qb < p.Qtot) {
+              if (p.dsplit > 0) {
+                if (h != c_hi) {
+                  const long long qh = h * nql * p.L;
+                  cbr = 1.0; cbi = 0.0;
+                  table_product<CPLX>(T, eo + pt, BM, p.qdig + (size_t)qh * p.DP, 0, p.dsplit - 1, cbr, cbi);
+                  c_hi = h;
+                  const long long qn = qh + (long long)nql * p.L;           // digit row of the next run: into L1 ahead of use
+                  if (qn < p.Qtot) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p.qdig + (size_t)qn * p.DP));
+                }
+                table_mul<CPLX>(T, eo_last + l, cbr, cbi, vr, vi);
+              } else vr = 1.0;
+            }
+            Pst[pb * SP + pt] = vr;
+            if (CPLX) Pst[(p.npfx + pb) * SP + pt] = vi;
+          }
+        }
+        if (pt < VKQ) {
+          const int t = rem + pt;                                          // offset from the first point of block blk
+          const int pb = t / p.L;
+          reinterpret_cast<int2 *>(st + IDX_OFF)[pt] = make_int2((t - pb * p.L) * SP, pb * SP);
+        }
+        mbar_arrive(&full[s]);
+        rem += VKQ;
+        while (rem >= p.L) { rem -= p.L; if (++lo == nql) { lo = 0; hi++; } }
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // =========================== CONSUMERS ===============================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(216));
+    const int rg = warp % RG, kg = warp / RG;
+    const int g = lane >> 2, kl = lane & 3;
+    const unsigned sgn = (g & 1) ? 0u : 0x80000000u;
+    const int rbase = rg * WM * 8 + g;
+    auto acc_pair = [&](const double (&ac)[WM][WN][2], int a, int idx, double &v0, double &v1, int &cc) {
+      if (PAIRED) { const int b2 = idx >> 1, e = idx & 1; v0 = ac[a][2 * b2][e]; v1 = ac[a][2 * b2 + (WN > 1 ? 1 : 0)][e]; cc = 16 * b2 + 4 * kl + 2 * e; }
+      else { v0 = ac[a][idx][0]; v1 = ac[a][idx][1]; cc = 8 * idx + 2 * kl; }
+    };
+    int s = 0, it = 0;
+    unsigned ph = 0;
+    for (int sidx = 0; sidx < nseg; sidx++) {
+      int tile, c0, c1, slot;
+      wk.segment(gcta, sidx, tile, c0, c1, slot);
+      const int tn = tile % p.tiles_n, tr = tile / p.tiles_n;
+      double acc[WM][WN][2];
+#pragma unroll
+      for (int a = 0; a < WM; a++)
+#pragma unroll
+        for (int b = 0; b < WN; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+      mbar_wait(s_full, (unsigned)sidx & 1u);
+      const double *Sr = S + rbase;
+      const double *Si = S + (size_t)p.L * SP + rbase;
+
+      for (int c = c0; c < c1; c++, it++) {
+        const bool mine = KG == 1 || (it & 1) == kg;
+        if (mine) {
+          mbar_wait(&full[s], ph);
+          const unsigned char *st = ring + (size_t)s * p.stage_bytes;
+          const double *bs = reinterpret_cast<const double *>(st) + g;
+          const double *bs2 = reinterpret_cast<const double *>(st) + 2 * g;
+          const double *Pr = reinterpret_cast<const double *>(st + P_OFF) + rbase;
+          const double *Pi = Pr + (size_t)p.npfx * SP;
+          const int2 *idx = reinterpret_cast<const int2 *>(st + IDX_OFF);
+          double last = 0.0;
+#pragma unroll
+          for (int ks = 0; ks < VKQ / 4; ks++) {
+            const int k = ks * 4 + kl;
+            const int2 ix = idx[k];
+            double are[WM], aim[WM];
+#pragma unroll
+            for (int a = 0; a < WM; a++) {
+              const double sr = Sr[ix.x + a * 8], pr = Pr[ix.y + a * 8];
+              if (!CPLX) are[a] = sr * pr;
+              else {
+                const double si = Si[ix.x + a * 8], pi = Pi[ix.y + a * 8];
+                are[a] = sr * pr - si * pi;
+                aim[a] = sr * pi + si * pr;
+              }
+            }
+            double bfr[WN], bsw[WN];
+            if (PAIRED) {
+#pragma unroll
+              for (int b2 = 0; b2 < WN / 2; b2++) {
+                const double2 v = *reinterpret_cast<const double2 *>(bs2 + k * LDB + 16 * b2);
+                bfr[2 * b2] = v.x; bfr[2 * b2 + 1] = v.y;
+                if (CPLX) { bsw[2 * b2] = flip_sign(v.y, 0x80000000u); bsw[2 * b2 + 1] = v.x; }
+              }
+            } else {
+#pragma unroll
+              for (int b = 0; b < WN; b++) {
+                bfr[b] = bs[k * LDB + b * 8];
+                if (CPLX) bsw[b] = flip_sign(bs[k * LDB + b * 8 + ((g & 1) ? -1 : 1)], sgn);
+              }
+            }
+#pragma unroll
+            for (int a = 0; a < WM; a++)
+#pragma unroll
+              for (int b = 0; b < WN; b++) {
+                dmma884(acc[a][b][0], acc[a][b][1], are[a], bfr[b]);
+                if (CPLX) dmma884(acc[a][b][0], acc[a][b][1], aim[a], bsw[b]);
+              }
+            if (ks == VKQ / 4 - 1) last = are[WM - 1] + bfr[WN - 1];
+          }
+          // release the stage: the arrive's address depends on the last fragment registers of the stage
+          const unsigned dep = (unsigned)__double2hiint(last) & p.zero;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s], dep);
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+
+      // ---- end of segment -------------------------------------------------------------------------
+      if (KG == 2) {
+        // the two k-groups hold partial sums of the same tile: group 1 hands its accumulators to group 0
+        double *x = xchg + ((size_t)rg * 32 + lane) * (WM * WN * 2);
+        if (kg == 1) {
+#pragma unroll
+          for (int a = 0; a < WM; a++)
+#pragma unroll
+            for (int b = 0; b < WN; b++) { x[(a * WN + b) * 2] = acc[a][b][0]; x[(a * WN + b) * 2 + 1] = acc[a][b][1]; }
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(VNCW * 32) : "memory");
+        if (kg == 0) {
+#pragma unroll
+          for (int a = 0; a < WM; a++)
+#pragma unroll
+            for (int b = 0; b < WN; b++) { acc[a][b][0] += x[(a * WN + b) * 2]; acc[a][b][1] += x[(a * WN + b) * 2 + 1]; }
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(VNCW * 32) : "memory");
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);            // this warp no longer reads S of the segment
+      if (KG == 2 && kg == 1) continue;
+      if (slot >= 0) {
+        double *wsp = p.sk_ws + ((size_t)gcta * 2 + slot) * (BM * BN);
+#pragma unroll
+        for (int a = 0; a < WM; a++)
+#pragma unroll
+          for (int b = 0; b < WN; b++) {
+            double v0, v1; int cc;
+            acc_pair(acc, a, b, v0, v1, cc);
+            *reinterpret_cast<double2 *>(wsp + (size_t)(rbase + a * 8) * BN + cc) = make_double2(v0, v1);
+          }
+      } else {
+#pragma unroll
+        for (int a = 0; a < WM; a++) {
+          const int r = tr * BM + rbase + a * 8;
+          if (r >= p.nk) continue;
+#pragma unroll
+          for (int b = 0; b < WN; b++) {
+            double v0, v1; int cc;
+            acc_pair(acc, a, b, v0, v1, cc);
+            const int col = tn * BN + cc;
+            double *dst = p.out + (size_t)r * p.ncols_d + col;
+            if (col + 1 < p.ncols_d && ((reinterpret_cast<size_t>(dst) & 15) == 0)) {
+              if (p.accumulate) { const double2 o = *reinterpret_cast<double2 *>(dst); v0 += o.x; v1 += o.y; }
+              *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
+            } else {
+              if (col < p.ncols_d) dst[0] = p.accumulate ? dst[0] + v0 : v0;
+              if (col + 1 < p.ncols_d) dst[1] = p.accumulate ? dst[1] + v1 : v1;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// adds the stream-K pieces of each remainder tile in CTA order and stores the tile.  grid = (remainder tiles, slices)
+__global__ void __launch_bounds__(256) k_vfixup(const __grid_constant__ VParams p, int G, int BM, int BN) {
+  const SkWork wk(G, p.tiles_r * p.tiles_n, p.nchunk);
+  const int rt = blockIdx.x, tile = wk.nfull * G + rt;
+  const int tn = tile % p.tiles_n, tr = tile / p.tiles_n;
+  const long long u0 = (long long)rt * wk.nchunk, u1 = u0 + wk.nchunk;
+  __shared__ int s_src[1024];
+  __shared__ int s_n;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int g = 0; g < G && n < 1024; g++) {
+      const long long a0 = wk.lo(g), a1 = wk.lo(g + 1);
+      if (a1 <= u0 || a1 <= a0) continue;
+      if (a0 >= u1) break;
+      s_src[n++] = g * 2 + ((a0 / wk.nchunk == rt) ? 0 : 1);
+    }
+    s_n = n;
+  }
+  __syncthreads();
+  const int npieces = s_n;
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < BM * BN; e += gridDim.y * blockDim.x) {
+    const int r = tr * BM + e / BN, col = tn * BN + e % BN;
+    if (r >= p.nk || col >= p.ncols_d) continue;
+    double sum = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < npieces; k++) sum += p.sk_ws[(size_t)s_src[k] * ((size_t)BM * BN) + e];
+    double *dst = p.out + (size_t)r * p.ncols_d + col;
+    *dst = p.accumulate ? *dst + sum : sum;
+  }
+}
+
+struct VVariant { int id, BM, BN; const char *name; };
+//                      WM WN RG KG
+typedef VTile<2, 1, 8, 1, false> V128x8;
+typedef VTile<2, 3, 8, 1, false> V128x24;
+typedef VTile<2, 4, 8, 1, false> V128x32;
+typedef VTile<2, 6, 8, 1, false> V128x48;
+typedef VTile<3, 1, 4, 2, false> V96x8;
+typedef VTile<3, 3, 4, 2, false> V96x24;
+typedef VTile<3, 4, 4, 2, false> V96x32;
+typedef VTile<3, 6, 4, 2, false> V96x48;
+typedef VTile<2, 2, 8, 1, true> ZV128x16;
+typedef VTile<2, 4, 8, 1, true> ZV128x32;
+typedef VTile<2, 6, 8, 1, true> ZV128x48;
+typedef VTile<3, 2, 4, 2, true> ZV96x16;
+typedef VTile<3, 4, 4, 2, true> ZV96x32;
+typedef VTile<3, 6, 4, 2, true> ZV96x48;
+const VVariant V_REAL[] = {{1, 128, 8, "128x8"}, {2, 128, 24, "128x24"}, {3, 128, 32, "128x32"}, {4, 128, 48, "128x48"},
+                           {5, 96, 8, "96x8 (2 k-groups)"}, {6, 96, 24, "96x24 (2 k-groups)"}, {7, 96, 32, "96x32 (2 k-groups)"},
+                           {8, 96, 48, "96x48 (2 k-groups)"}};
+const VVariant V_CPLX[] = {{1, 128, 16, "128x16"}, {2, 128, 32, "128x32"}, {3, 128, 48, "128x48"},
+                           {4, 96, 16, "96x16 (2 k-groups)"}, {5, 96, 32, "96x32 (2 k-groups)"}, {6, 96, 48, "96x48 (2 k-groups)"}};
+
+struct VPlan {
+  int vi;                        // index into V_REAL / V_CPLX
+  int tiles_r, tiles_n, nchunk, grid, rem_tiles;
+  int dsplit, L, npfx, stages, stage_bytes;
+  size_t smem, ws_bytes;
+};
+
+int sm_count_v(int device) {
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+  return n;
+}
+
+template <class TL> void size_ring(const pspace_ctx *c, VPlan &pl) {
+  // tail = as many trailing variables as keep S within its budget; the ring gets what is left of the 227 KB
+  const size_t budget = 72 * 1024;
+  int ds = c->nvars;
+  long long L = 1;
+  while (ds > 0) {
+    const long long Ln = L * c->nq[ds - 1];
+    if (TL::s_bytes((int)std::min<long long>(Ln, 1 << 20)) > budget || Ln > (1 << 20)) break;
+    L = Ln; ds--;
+  }
+  if (ds == c->nvars) { ds = c->nvars - 1; L = c->nq[ds]; }      // a single rule (<= 20 points) always fits
+  pl.dsplit = ds; pl.L = (int)L;
+  pl.npfx = (int)((VKQ + L - 2) / L) + 1;
+  pl.stage_bytes = TL::stage_bytes(pl.npfx);
+  const size_t head = TL::header_bytes(pl.L, c->nvars, c->tsz);
+  const size_t avail = (size_t)227 * 1024 - head - 1024 - 256;
+  pl.stages = (int)std::max<size_t>(2, std::min<size_t>(8, avail / pl.stage_bytes));
+  pl.smem = head + (size_t)pl.stages * pl.stage_bytes + (2 * pl.stages + 2) * 8 + 1024;
+}
+
+template <class TL> int launch_v(const pspace_ctx *c, VParams &p, const VPlan &pl, const double *d_in, cudaStream_t st) {
+  CUtensorMap tmB;
+  {
+    unsigned long long dims[2] = {(unsigned long long)p.ncols_d, (unsigned long long)(p.q1 - p.q0)};
+    unsigned long long str[1] = {(unsigned long long)p.ncols_d * 8};
+    unsigned box[2] = {(unsigned)TL::LDB, (unsigned)VKQ};
+    int rc = ps_make_tmap(&tmB, d_in, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  if (pl.smem > (size_t)227 * 1024) return ps_fail(PSPACE_EINVAL, "vector projection: %zu bytes of shared memory", pl.smem);
+  PS_CUDA(cudaFuncSetAttribute(k_project_vf<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  k_project_vf<TL><<<pl.grid, VT, pl.smem, st>>>(p, tmB);
+  PS_LAUNCH_CHECK(c);
+  if (pl.rem_tiles > 0) {
+    const int split = std::max(1, std::min((TL::BM * TL::BN) / 256, (2 * pl.grid + pl.rem_tiles - 1) / pl.rem_tiles));
+    k_vfixup<<<dim3(pl.rem_tiles, split), 256, 0, st>>>(p, pl.grid, TL::BM, TL::BN);
+    PS_LAUNCH_CHECK(c);
+  }
+  return PSPACE_OK;
+}
+
+int plan_v(const pspace_ctx *c, const pspace_project_args *a, VPlan &pl) {
+  const int ncols_d = a->ncols * c->width, nk = a->k1 - a->k0;
+  const VVariant *vs = c->is_complex ? V_CPLX : V_REAL;
+  const int nv = c->is_complex ? 6 : 8;
+  int best = -1;
+  if (a->variant > 0) {
+    for (int i = 0; i < nv; i++) if (vs[i].id == a->variant) best = i;
+    if (best < 0) return ps_fail(PSPACE_EINVAL, "unknown vector tile variant %d", a->variant);
+  } else {
+    // fewest column tiles first (every column tile regenerates the operand), then the least padded work
+    long long best_tn = 0, best_cost = 0;
+    for (int i = 0; i < nv; i++) {
+      const long long tn = (ncols_d + vs[i].BN - 1) / vs[i].BN, trr = (nk + vs[i].BM - 1) / vs[i].BM;
+      const long long cost = tn * vs[i].BN * trr * vs[i].BM;
+      if (best < 0 || tn < best_tn || (tn == best_tn && cost < best_cost)) { best = i; best_tn = tn; best_cost = cost; }
+    }
+  }
+  pl.vi = best;
+  pl.tiles_n = (ncols_d + vs[best].BN - 1) / vs[best].BN;
+  pl.tiles_r = (nk + vs[best].BM - 1) / vs[best].BM;
+  pl.nchunk = (int)((a->q1 - a->q0 + VKQ - 1) / VKQ);
+  const long long ntiles = (long long)pl.tiles_r * pl.tiles_n;
+  pl.grid = (int)std::max<long long>(1, std::min<long long>(sm_count_v(c->device), ntiles * pl.nchunk));
+  pl.rem_tiles = (int)(ntiles % pl.grid);
+  pl.ws_bytes = pl.rem_tiles > 0 ? (size_t)pl.grid * 2 * vs[best].BM * vs[best].BN * sizeof(double) : 0;
+  return PSPACE_OK;
+}
+}  // namespace
+
+// workspace of the factored vector projection (0 when every tile is a full one)
+size_t ps_vproject_workspace(const pspace_ctx *c, const pspace_project_args *a) {
+  VPlan pl;
+  if (a->k1 <= a->k0 || a->q1 <= a->q0 || plan_v(c, a, pl) != PSPACE_OK) return 0;
+  return pl.ws_bytes;
+}
+
+// true when the factored kernel can take the call (TMA-addressable f: even real column count, 16-byte aligned base)
+bool ps_vproject_usable(const pspace_ctx *c, const pspace_project_args *a, const double *d_in) {
+  const int ncols_d = a->ncols * c->width;
+  return !c->force_generic && !c->force_panel && (ncols_d % 2) == 0 && (reinterpret_cast<size_t>(d_in) % 16) == 0 && c->d_Tw &&
+         c->tsz + PSPACE_MAX_NQ < 65536;
+}
+
+int ps_vproject(const pspace_ctx *c, const pspace_project_args *a, const double *d_in, double *d_out, void *d_ws,
+                size_t ws_bytes, cudaStream_t st) {
+  VPlan pl;
+  int rc = plan_v(c, a, pl);
+  if (rc) return rc;
+  if (pl.ws_bytes > ws_bytes || (pl.ws_bytes && !d_ws))
+    return ps_fail(PSPACE_EINVAL, "workspace of %zu bytes needed, %zu given", pl.ws_bytes, ws_bytes);
+  VParams p;
+  p.out = d_out; p.sk_ws = (double *)d_ws;
+  p.Tw = c->d_Tw; p.deg = c->d_deg; p.qdig = c->d_qdig;
+  p.q0 = a->q0; p.q1 = a->q1; p.Qtot = c->Q;
+  p.k0 = a->k0; p.nk = a->k1 - a->k0; p.ncols_d = a->ncols * c->width; p.nvars = c->nvars; p.DP = c->DP; p.tsz = c->tsz;
+  for (int d = 0; d < PSPACE_MAX_VARS; d++) { p.toff[d] = d < c->nvars ? c->toff[d] : 0; p.nq[d] = d < c->nvars ? c->nq[d] : 1; }
+  p.tiles_r = pl.tiles_r; p.tiles_n = pl.tiles_n; p.nchunk = pl.nchunk;
+  p.accumulate = a->accumulate; p.zero = 0;
+  const VVariant &v = (c->is_complex ? V_CPLX : V_REAL)[pl.vi];
+  const int key = (c->is_complex ? 100 : 0) + v.id;
+#define PS_VCASE(K, TL)                                                                              \
+  case K:                                                                                            \
+    size_ring<TL>(c, pl);                                                                            \
+    p.dsplit = pl.dsplit; p.L = pl.L; p.npfx = pl.npfx; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; \
+    rc = launch_v<TL>(c, p, pl, d_in, st);                                                           \
+    break;
+  switch (key) {
+    PS_VCASE(1, V128x8) PS_VCASE(2, V128x24) PS_VCASE(3, V128x32) PS_VCASE(4, V128x48)
+    PS_VCASE(5, V96x8) PS_VCASE(6, V96x24) PS_VCASE(7, V96x32) PS_VCASE(8, V96x48)
+    PS_VCASE(101, ZV128x16) PS_VCASE(102, ZV128x32) PS_VCASE(103, ZV128x48)
+    PS_VCASE(104, ZV96x16) PS_VCASE(105, ZV96x32) PS_VCASE(106, ZV96x48)
+    default: rc = ps_fail(PSPACE_EINVAL, "no vector kernel for key %d", key);
+  }
+#undef PS_VCASE
+  if (rc) return rc;
+  pspace_ctx *mc = const_cast<pspace_ctx *>(c);
+  mc->plan_kernel = "factored operand (P x S in shared memory), tma + mbarrier warp-specialised, persistent stream-K";
+  mc->plan_chunk_pts = VKQ;
+  mc->plan_flop = 2.0 * (double)p.nk * (double)p.ncols_d * (double)(a->q1 - a->q0) * (c->is_complex ? 2.0 : 1.0);
+  char buf[320];
+  snprintf(buf, sizeof buf, "%sdmma vec %s [%s] tiles=%dx%d chunks=%d ctas=%d streamk_tiles=%d tail=%d vars (L=%d) stages=%d scratch=%zu",
+           c->is_complex ? "z " : "", v.name, c->plan_kernel, pl.tiles_r, pl.tiles_n, pl.nchunk, pl.grid, pl.rem_tiles,
+           c->nvars - pl.dsplit, pl.L, pl.stages, pl.ws_bytes);
+  mc->plan = buf;
+  return PSPACE_OK;
+}

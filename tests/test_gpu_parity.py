@@ -225,9 +225,15 @@ def test_every_tile_variant_matches():
         C = c.projectMatrix(Jd, 0, 20, 3, 30, variant=variant).cpu().numpy()
         assert normwise(C, ref) < TOL, variant
     refF = o.project_vector(J)
+    for variant in range(1, 9):                      # factored-operand kernel: 128- and 96-row tiles x 8/24/32/48 columns
+        F = c.projectVector(Jd, variant=variant).cpu().numpy()
+        assert normwise(F, refF) < TOL, variant
+        assert "factored" in c.lastPlan()
+    c.setOption("force_panel", 1)                    # round-1 panel kernels
     for variant in (1, 2, 3):
         F = c.projectVector(Jd, variant=variant).cpu().numpy()
         assert normwise(F, refF) < TOL, variant
+        assert "factored" not in c.lastPlan()
     c.close()
 
 
@@ -288,6 +294,67 @@ def test_expansion_evaluation_vs_oracle(cplx):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
+def test_factored_operand_kernels_vs_oracle_and_panel_kernels(cplx):
+    """Vector projection and expansion evaluation through the factored-operand kernels (psi = prefix x tail, formed
+    in shared memory; no basis panel): every tile variant, rule sizes that do not divide the 64-point stage (tail
+    lengths 3, 5, 15, 20, 36 ...), q-windows that start inside a tail run, basis windows, accumulate, a one-variable
+    container (empty prefix), and agreement with the round-1 panel kernels on the same input."""
+    rng = np.random.default_rng(123 + cplx)
+    pert = 1e-30j if cplx else 0.0
+    containers = [
+        ([("normal", 0.3 + pert, 1.2, 3), ("uniform", -1.0, 2.0, 2), ("exponential", 0.0, 0.5, 4), ("normal", 1.0, 0.4, 2)], 1, None),
+        ([("uniform", 0.0, 1.0 + pert, 5), ("normal", 0.0, 1.0, 5), ("exponential", 1.0, 0.5, 5)], 0, None),      # nq = 6: L = 36
+        ([("normal", 0.5 + pert, 1.5, 19)], 0, None),                                                       # one rule of 20 points
+        ([("normal", 0.0, 1.0, 1), ("uniform", 0.0, 1.0, 1), ("exponential", 0.0, 1.0, 1)] * 3, 1, None),     # 9 variables, nq = 2
+        ([("uniform", -1.0, 1.0, 2), ("normal", 0.2, 0.7 + pert, 2), ("exponential", 0.0, 1.0, 2)], 0, [7, 3, 5]),  # nq != dmax+1
+    ]
+    nvar_v = 6 if cplx else 8
+    for ps, bt, nq in containers:
+        o = H.CpuContainer(H.oracle_api(cplx), ps, bt).initialize()
+        c = _dc(ps, bt, cplx).initialize()
+        if nq is not None:
+            o.initialize_quadrature(np.array(nq, dtype=np.intc))
+            c.initializeQuadrature(nq)
+        assert (c.N, c.Q) == (o.N, o.Q)
+        tol = 5e-11 if len(ps) == 1 else TOL
+        for m in (2, 12, 24, 26):
+            f = rng.normal(size=(o.Q, m)).astype(o.dtype)
+            V = rng.normal(size=(o.N, m)).astype(o.dtype)
+            if cplx:
+                f = f + 1j * rng.normal(size=f.shape)
+                V = V + 1j * rng.normal(size=V.shape)
+            fd, Vd = torch.from_numpy(f).cuda(), torch.from_numpy(V).cuda()
+            refF, refU = o.project_vector(f), o.evaluate_expansion(V)
+            for variant in range(0, nvar_v + 1):
+                F = c.projectVector(fd, variant=variant)
+                assert "factored" in c.lastPlan()
+                assert normwise(F.cpu().numpy(), refF) < tol, (ps, m, variant)
+            U = c.evaluateExpansion(Vd)
+            assert "factored" in c.lastPlan()
+            assert normwise(U.cpu().numpy(), refU) < tol, (ps, m)
+            # windows: q range starting inside a tail run / ending ragged, basis sub-range, accumulate
+            q0, q1 = (1, o.Q - 1) if o.Q > 4 else (0, o.Q)
+            k0, k1 = (1, o.N - 1) if o.N > 3 else (0, o.N)
+            Fw = c.projectVector(fd[q0:q1].contiguous(), k0, k1, q0=q0, q1=q1)
+            fz = f.copy()
+            fz[:q0] = 0
+            fz[q1:] = 0                                           # the oracle sums over all q: zero rows outside the window
+            assert normwise(Fw.cpu().numpy(), o.project_vector(fz, k0, k1)) < tol, (ps, m)
+            Fa = c.projectVector(fd[q0:q1].contiguous(), k0, k1, q0=q0, q1=q1, out=Fw.clone(), accumulate=True)
+            assert normwise(Fa.cpu().numpy(), 2 * Fw.cpu().numpy()) < 1e-15
+            Uw = c.evaluateExpansion(Vd[k0:k1].contiguous(), k0, k1, q0, q1)
+            assert normwise(Uw.cpu().numpy(), o.evaluate_expansion(V[k0:k1], k0, k1, q0, q1)) < tol, (ps, m)
+            Ua = c.evaluateExpansion(Vd[k0:k1].contiguous(), k0, k1, q0, q1, out=Uw.clone(), accumulate=True)
+            assert normwise(Ua.cpu().numpy(), 2 * Uw.cpu().numpy()) < 1e-15
+            # the panel kernels of round 1 on the same input
+            c.setOption("force_panel", 1)
+            Fp, Up = c.projectVector(fd), c.evaluateExpansion(Vd)
+            c.setOption("force_panel", 0)
+            assert normwise(Fp.cpu().numpy(), F.cpu().numpy()) < 1e-13 and normwise(Up.cpu().numpy(), U.cpu().numpy()) < 1e-13
+        c.close()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
 def test_basis_panel_is_bit_identical_to_batched_basis(cplx):
     """The q-major panel kernel (k_psi_panel: prefix product over the slow variables kept per thread) must produce the
     very values of the k-major batched evaluation (k_eval_basis_grid): expanding the identity returns the panel itself
@@ -301,7 +368,13 @@ def test_basis_panel_is_bit_identical_to_batched_basis(cplx):
         dt = torch.complex128 if cplx else torch.float64
         eye = torch.eye(c.N, dtype=dt, device="cuda")
         psi = c.evalBasisGrid()                                  # [N][Q]
+        # the factored-operand kernel multiplies (prefix product) x (tail product): same factors, other association
+        Uf = c.evaluateExpansion(eye)
+        assert ("factored" in c.lastPlan()) == (c.N * (2 if cplx else 1) % 2 == 0)     # odd real column counts: panel kernel
+        assert normwise(Uf.cpu().numpy(), psi.T.cpu().numpy()) < 1e-15, ps
+        c.setOption("force_panel", 1)
         U = c.evaluateExpansion(eye)                             # [Q][N]
+        assert "panel" in c.lastPlan()
 
         def same(a, b):      # real: pure products in the same order; complex: the panel kernel contracts to FMAs
             return torch.equal(a, b) if not cplx else normwise(a.cpu().numpy(), b.cpu().numpy()) < 1e-14
@@ -343,8 +416,9 @@ def test_tacs_layouts_and_pair_mask_bit_exact(cplx):
     c.close()
 
 
+@pytest.mark.parametrize("force_panel", [0, 1])
 @pytest.mark.parametrize("cplx", [False, True])
-def test_panel_cache_slots_reuse_and_invalidate(cplx):
+def test_panel_cache_slots_reuse_and_invalidate(cplx, force_panel):
     """The two panel slots (unweighted rows: expansion + i side; weighted rows: j side) are reused when a call repeats
     their (row range, q-range) and rebuilt otherwise: an interleaved sequence of expansions, vector and matrix
     projections with the cache on must return bit-for-bit what the same calls return with the cache off, also across
@@ -352,6 +426,7 @@ def test_panel_cache_slots_reuse_and_invalidate(cplx):
     rng = np.random.default_rng(91)
     ps = [("normal", 0.3 + (1e-30j if cplx else 0), 1.2, 3), ("exponential", 0.0, 0.5, 2), ("uniform", -1.0, 2.0, 3)]
     c = _dc(ps, 0, cplx).initialize()
+    c.setOption("force_panel", force_panel)      # 1: the one-pass operators use the panel slots too (round-1 kernels)
     dt = torch.complex128 if cplx else torch.float64
 
     def operands():
