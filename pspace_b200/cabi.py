@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpspace_cuda.so")
+LIB_PATH = os.environ.get("PSPACE_CUDA_LIB") or os.path.join(_HERE, "lib", "libpspace_cuda.so")   # override: kernel experiments
 
 _vp, _i, _ll, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t
 _ull, _dbl = ctypes.c_ulonglong, ctypes.c_double

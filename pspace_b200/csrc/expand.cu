@@ -18,6 +18,7 @@
 #include "ctx.h"
 #include "factored.cuh"
 #include <algorithm>
+#include <atomic>
 #include <stdio.h>
 
 namespace {
@@ -174,25 +175,34 @@ struct XFParams {
   int k0, nk, ncols_d, nvars, DP, tsz;
   int toff[PSPACE_MAX_VARS], nq[PSPACE_MAX_VARS];
   int dsplit, L, npfx;
+  int resident;                // 1: the tail table S of ALL basis rows (and their table offsets) stays in shared memory
   int tiles_n, nkc, stages, stage_bytes;
   int accumulate;
   unsigned zero;
 };
 
-template <int WM_, int WN_, bool CPLX_> struct XTile {
+template <int WM_, int WN_, bool CPLX_, int KC_> struct XTile {
   static constexpr int WM = WM_, WN = WN_;
   static constexpr bool CPLX = CPLX_;
   static constexpr int W = CPLX ? 2 : 1;
   static constexpr int BQ = XNCW * WM * 8, BN = WN * 8, LDB = BN + 4;
-  static constexpr int KC = CPLX ? 64 : 128;       // basis rows per pipeline stage
+  static constexpr int KC = KC_;                   // basis rows per pipeline stage (128, 64 or 32)
   static constexpr int KCP = KC + 4;               // == 4 (mod 16): conflict-free S reads (row g -> consecutive tail points)
   static constexpr int TPR = XNPT / KC;            // producer threads per basis row
   static constexpr int V_BYTES = KC * LDB * 8;
   static_assert(LDB % 16 == 4 || LDB % 16 == 12, "V pitch");
-  __host__ __device__ static int stage_bytes(int L, int npfx) { return (V_BYTES + W * (L + npfx) * KCP * 8 + 127) / 128 * 128; }
-  __host__ __device__ static size_t eo_bytes(int nvars) { return ((size_t)TPR * nvars * KC * 2 + 15) & ~(size_t)15; }
+  // shared-memory header: table offsets of the rows, the 1-D tables, (resident mode) S of all rows
+  __host__ __device__ static size_t eo_bytes(int nvars, int nkc, int res) {
+    return ((size_t)(res ? nkc * KC : TPR * KC) * nvars * 2 + 15) & ~(size_t)15;
+  }
   __host__ __device__ static size_t tab_bytes(int tsz) { return tsz <= psf::TAB_SMEM_MAX ? (size_t)tsz * W * 8 : 0; }
-  __host__ __device__ static size_t header_bytes(int nvars, int tsz) { return (eo_bytes(nvars) + tab_bytes(tsz) + 127) / 128 * 128; }
+  __host__ __device__ static size_t sres_bytes(int L, int nkc, int res) { return res ? (size_t)W * L * (nkc * KC + 4) * 8 : 0; }
+  __host__ __device__ static size_t header_bytes(int nvars, int tsz, int L, int nkc, int res) {
+    return (eo_bytes(nvars, nkc, res) + tab_bytes(tsz) + sres_bytes(L, nkc, res) + 127) / 128 * 128;
+  }
+  __host__ __device__ static int stage_bytes(int L, int npfx, int res) {
+    return (V_BYTES + W * ((res ? 0 : L) + npfx) * KCP * 8 + 127) / 128 * 128;
+  }
 };
 
 template <class TL>
@@ -201,23 +211,36 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
   constexpr bool CPLX = TL::CPLX;
   constexpr bool PAIRED = CPLX && (WN % 2) == 0;
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned short *eo_all = reinterpret_cast<unsigned short *>(smem);                  // [TPR][nvars][KC] producer scratch
-  double *Ts = reinterpret_cast<double *>(smem + TL::eo_bytes(p.nvars));
-  unsigned char *ring = smem + TL::header_bytes(p.nvars, p.tsz);
+  const int RES = p.resident, NR = p.nkc * KC, NRP = NR + 4;
+  unsigned short *eo_all = reinterpret_cast<unsigned short *>(smem);        // resident: [nvars][NR]; else [TPR][nvars][KC]
+  double *Ts = reinterpret_cast<double *>(smem + TL::eo_bytes(p.nvars, p.nkc, RES));
+  double *S_res = reinterpret_cast<double *>(smem + TL::eo_bytes(p.nvars, p.nkc, RES) + TL::tab_bytes(p.tsz));   // [W][L][NRP]
+  unsigned char *ring = smem + TL::header_bytes(p.nvars, p.tsz, p.L, p.nkc, RES);
   const int STAGES = p.stages;
   unsigned long long *full = reinterpret_cast<unsigned long long *>(ring + (size_t)STAGES * p.stage_bytes);
   unsigned long long *empty = full + STAGES;
-  const int S_OFF = TL::V_BYTES, P_OFF = TL::V_BYTES + W * p.L * KCP * 8;
+  const int S_OFF = TL::V_BYTES, P_OFF = TL::V_BYTES + (RES ? 0 : W * p.L * KCP * 8);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long ntiles = p.tiles_q * p.tiles_n;
   const bool tab_smem = p.tsz <= TAB_SMEM_MAX;
   if (tab_smem)
     for (int i = tid; i < p.tsz * W; i += XFT) Ts[i] = p.T[i];
   const double *T = tab_smem ? Ts : p.T;
+  const int nq_tail = p.nq[p.nvars - 1], nq_pfx = p.dsplit > 0 ? p.nq[p.dsplit - 1] : 1;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1 + XNPT); mbar_init(&empty[s], XNCW); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (RES) {
+    // once per CTA: table offsets and the tail table of every basis row (a thread owns a row; it reads the tables from
+    // global memory here — the shared-memory copy is being written by other threads)
+    for (int r = tid; r < NR; r += XFT) {
+      const bool valid = r < p.nk;
+      for (int d = 0; d < p.nvars; d++)
+        eo_all[d * NR + r] = (unsigned short)(valid ? p.toff[d] + __ldg(p.deg + (size_t)(p.k0 + r) * p.nvars + d) * p.nq[d] : 0);
+      run_products<CPLX>(p.T, eo_all + r, NR, p.qdig, p.DP, 0, p.L, 1, p.Qtot, p.dsplit, p.nvars, nq_tail, valid, S_res + r, NRP, p.L);
+    }
   }
   __syncthreads();
 
@@ -225,8 +248,10 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
     // =========================== PRODUCERS ================================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(56));
     const int pt = tid - XNCW * 32, r = pt % KC, sub = pt / KC;
-    unsigned short *eo = eo_all + (size_t)sub * p.nvars * KC + r;      // my own copy of the row's table offsets, stride KC
     if (pt == 0) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmapV) : "memory");
+    // entries of a stage: npfx prefix values, then (streamed mode) L tail values per row; the TPR threads of a row split them
+    const int ne = p.npfx + (RES ? 0 : p.L), per = (ne + TL::TPR - 1) / TL::TPR;
+    const int e_lo = sub * per, e_hi = min(ne, e_lo + per);
     int s = 0;
     unsigned ph = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -241,9 +266,6 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
           if (qn < p.Qtot) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p.qdig + (size_t)qn * p.DP));
         }
       }
-      // entries of a stage: npfx prefix values then L tail values per row; the TPR threads of a row split them in halves
-      const int ne = p.npfx + p.L;
-      const int e_lo = sub * ((ne + TL::TPR - 1) / TL::TPR), e_hi = min(ne, e_lo + (ne + TL::TPR - 1) / TL::TPR);
       for (int kc = 0; kc < p.nkc; kc++) {
         mbar_wait(&empty[s], ph ^ 1u);
         unsigned char *st = ring + (size_t)s * p.stage_bytes;
@@ -253,19 +275,25 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
         }
         const int kr = kc * KC + r;
         const bool valid = kr < p.nk;
-        const int k = p.k0 + kr;
-        if (valid)
-          for (int d = 0; d < p.nvars; d++)
-            eo[d * KC] = (unsigned short)(p.toff[d] + __ldg(p.deg + (size_t)k * p.nvars + d) * p.nq[d]);
+        const unsigned short *eo;
+        int eos;
+        if (RES) { eo = eo_all + kr; eos = NR; }
+        else {
+          unsigned short *mine = eo_all + (size_t)sub * p.nvars * KC + r;      // my own copy of the row's offsets
+          if (valid)
+            for (int d = 0; d < p.nvars; d++)
+              mine[d * KC] = (unsigned short)(p.toff[d] + __ldg(p.deg + (size_t)(p.k0 + kr) * p.nvars + d) * p.nq[d]);
+          eo = mine; eos = KC;
+        }
         double *Sst = reinterpret_cast<double *>(st + S_OFF), *Pst = reinterpret_cast<double *>(st + P_OFF);
         if (e_lo < p.npfx) {
           const int n = min(e_hi, p.npfx) - e_lo;
-          run_products<CPLX>(T, eo, KC, p.qdig, p.DP, blk0 + e_lo, n, p.L, p.Qtot, 0, p.dsplit,
-                             p.dsplit > 0 ? p.nq[p.dsplit - 1] : 1, valid, Pst + e_lo * KCP + r, KCP, p.npfx);
+          run_products<CPLX>(T, eo, eos, p.qdig, p.DP, blk0 + e_lo, n, p.L, p.Qtot, 0, p.dsplit, nq_pfx, valid,
+                             Pst + e_lo * KCP + r, KCP, p.npfx);
         }
         if (e_hi > p.npfx) {
           const int t0 = max(e_lo, p.npfx) - p.npfx, n = e_hi - p.npfx - t0;
-          run_products<CPLX>(T, eo, KC, p.qdig, p.DP, t0, n, 1, p.Qtot, p.dsplit, p.nvars, p.nq[p.nvars - 1], valid,
+          run_products<CPLX>(T, eo, eos, p.qdig, p.DP, t0, n, 1, p.Qtot, p.dsplit, p.nvars, nq_tail, valid,
                              Sst + t0 * KCP + r, KCP, p.L);
         }
         mbar_arrive(&full[s]);
@@ -277,6 +305,7 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(216));
     const int g = lane >> 2, kl = lane & 3;
     const unsigned sgn = (g & 1) ? 0u : 0x80000000u;
+    const int spitch = RES ? NRP : KCP;
     auto acc_pair = [&](const double (&ac)[WM][WN][2], int a, int idx, double &v0, double &v1, int &cc) {
       if (PAIRED) { const int b2 = idx >> 1, e = idx & 1; v0 = ac[a][2 * b2][e]; v1 = ac[a][2 * b2 + (WN > 1 ? 1 : 0)][e]; cc = 16 * b2 + 4 * kl + 2 * e; }
       else { v0 = ac[a][idx][0]; v1 = ac[a][idx][1]; cc = 8 * idx + 2 * kl; }
@@ -293,7 +322,7 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
         long long qa = qt0 + warp * (WM * 8) + a * 8 + g;
         if (qa >= p.q1) qa = p.q1 - 1;                               // rows past the range are computed on a valid point and not stored
         const long long b = qa / p.L;
-        soff[a] = (int)(qa - b * p.L) * KCP + kl;
+        soff[a] = (int)(qa - b * p.L) * spitch + kl;
         poff[a] = (int)(b - blk0) * KCP + kl;
       }
       double acc[WM][WN][2];
@@ -307,7 +336,8 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
         const unsigned char *st = ring + (size_t)s * p.stage_bytes;
         const double *bs = reinterpret_cast<const double *>(st) + kl * LDB + g;
         const double *bs2 = reinterpret_cast<const double *>(st) + kl * LDB + 2 * g;
-        const double *Sr = reinterpret_cast<const double *>(st + S_OFF), *Si = Sr + (size_t)p.L * KCP;
+        const double *Sr = RES ? S_res + kc * KC : reinterpret_cast<const double *>(st + S_OFF);
+        const double *Si = Sr + (size_t)p.L * spitch;
         const double *Pr = reinterpret_cast<const double *>(st + P_OFF), *Pi = Pr + (size_t)p.npfx * KCP;
         const int ksteps = (min(KC, p.nk - kc * KC) + 3) >> 2;
         int depi = 0;
@@ -378,29 +408,44 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
   }
 }
 
-template <class TL> int launch_expand_f(const pspace_ctx *c, XFParams &p, const double *d_V, cudaStream_t st) {
-  // tail length: the candidate (product of trailing rule sizes) with the fewest table products per stage,
-  // (prefix blocks of a tile) * dsplit + L * (nvars - dsplit), that leaves room for >= 2 stages
-  const size_t head = TL::header_bytes(c->nvars, c->tsz), avail = (size_t)227 * 1024 - head - 1024 - 256;
-  int best_ds = -1, best_L = 1, best_npfx = 0;
-  double best_cost = 0;
+// Tail length = a product of trailing rule sizes.  A (stage rows KC, tail length, resident?) candidate is rated by the table
+// products a producer thread makes per stage — the prefix entries of a tile, plus, unless the tail table of all rows fits in
+// shared memory next to two stages ("resident"), the L tail entries; an entry of a run costs ~1 + (variables - 1)/rule size
+// products — relative to the consumers' k-steps per stage.
+struct XFChoice { int ds, L, npfx, res; double score; };
+template <class TL> XFChoice plan_expand_f(const pspace_ctx *c, int nk) {
+  const int nkc = (nk + TL::KC - 1) / TL::KC;
+  const size_t cap = (size_t)227 * 1024 - 1024 - 256;
+  XFChoice best = {-1, 1, 0, 0, 0.0};
   long long L = 1;
   for (int ds = c->nvars; ds >= 0; ds--) {
     if (ds < c->nvars) L *= c->nq[ds];
     if (L > 4096) break;
     const int npfx = (int)((TL::BQ + L - 2) / L) + 1;
-    if ((size_t)TL::stage_bytes((int)L, npfx) * 2 > avail) continue;
-    const double cost = (double)npfx * ds + (double)L * (c->nvars - ds);
-    if (best_ds < 0 || cost < best_cost) { best_ds = ds; best_L = (int)L; best_npfx = npfx; best_cost = cost; }
+    const double c_pfx = npfx * (ds > 0 ? 1.0 + (double)(ds - 1) / c->nq[ds - 1] : 0.0);
+    const double c_tail = (double)L * (ds < c->nvars ? 1.0 + (double)(c->nvars - ds - 1) / c->nq[c->nvars - 1] : 0.0);
+    for (int res = 1; res >= 0; res--) {
+      const size_t need = TL::header_bytes(c->nvars, c->tsz, (int)L, nkc, res) + 2 * (size_t)TL::stage_bytes((int)L, npfx, res);
+      if (need > cap || (res && (size_t)nkc * TL::KC > 8192)) continue;
+      const double score = (c_pfx + (res ? 0.0 : c_tail) + 4.0) / TL::TPR / (TL::KC / 4);
+      if (best.ds < 0 || score < best.score) best = {ds, (int)L, npfx, res, score};
+    }
   }
-  if (best_ds < 0) return ps_fail(PSPACE_EINVAL, "evaluate_expansion: no factorisation fits shared memory");
-  p.dsplit = best_ds; p.L = best_L; p.npfx = best_npfx;
-  p.stage_bytes = TL::stage_bytes(p.L, p.npfx);
-  p.stages = (int)std::max<size_t>(2, std::min<size_t>(6, avail / p.stage_bytes));
+  return best;
+}
+
+template <class TL> int launch_expand_f(const pspace_ctx *c, XFParams &p, const double *d_V, cudaStream_t st) {
+  p.nkc = (p.nk + TL::KC - 1) / TL::KC;
+  const size_t cap = (size_t)227 * 1024 - 1024 - 256;
+  const XFChoice ch = plan_expand_f<TL>(c, p.nk);
+  if (ch.ds < 0) return ps_fail(PSPACE_EINVAL, "evaluate_expansion: no factorisation fits shared memory");
+  p.dsplit = ch.ds; p.L = ch.L; p.npfx = ch.npfx; p.resident = ch.res;
+  p.stage_bytes = TL::stage_bytes(p.L, p.npfx, p.resident);
+  const size_t head = TL::header_bytes(c->nvars, c->tsz, p.L, p.nkc, p.resident);
+  p.stages = (int)std::max<size_t>(2, std::min<size_t>(6, (cap - head) / p.stage_bytes));
   const size_t smem = head + (size_t)p.stages * p.stage_bytes + 2 * p.stages * 8 + 1024;
   p.tiles_q = (p.q1 - p.q0 + TL::BQ - 1) / TL::BQ;
   p.tiles_n = (p.ncols_d + TL::BN - 1) / TL::BN;
-  p.nkc = (p.nk + TL::KC - 1) / TL::KC;
   CUtensorMap tmV;
   {
     unsigned long long dims[2] = {(unsigned long long)p.ncols_d, (unsigned long long)p.nk};
@@ -412,13 +457,17 @@ template <class TL> int launch_expand_f(const pspace_ctx *c, XFParams &p, const 
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
   const int grid = (int)std::max<long long>(1, std::min<long long>(nsm, p.tiles_q * p.tiles_n));
-  PS_CUDA(cudaFuncSetAttribute(k_expand_f<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  static std::atomic<bool> attr_dev[64];        // per instantiation and device; setting it twice is harmless
+  if (!attr_dev[c->device & 63].load(std::memory_order_acquire)) {
+    PS_CUDA(cudaFuncSetAttribute(k_expand_f<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_dev[c->device & 63].store(true, std::memory_order_release);
+  }
   k_expand_f<TL><<<grid, XFT, smem, st>>>(p, tmV);
   PS_LAUNCH_CHECK(c);
   pspace_ctx *mc = const_cast<pspace_ctx *>(c);
   char buf[256];
-  snprintf(buf, sizeof buf, "%sexpand %dx%d factored operand: tail=%d vars (L=%d) prefix slots=%d KC=%d stages=%d ctas=%d", TL::CPLX ? "z " : "",
-           TL::BQ, TL::BN, c->nvars - p.dsplit, p.L, p.npfx, TL::KC, p.stages, grid);
+  snprintf(buf, sizeof buf, "%sexpand %dx%d factored operand: tail=%d vars (L=%d%s) prefix slots=%d KC=%d stages=%d ctas=%d", TL::CPLX ? "z " : "",
+           TL::BQ, TL::BN, c->nvars - p.dsplit, p.L, p.resident ? ", tail table resident" : "", p.npfx, TL::KC, p.stages, grid);
   mc->plan = buf;
   mc->plan_flop = 2.0 * (double)p.nk * (double)p.ncols_d * (double)(p.q1 - p.q0) * (TL::CPLX ? 2.0 : 1.0);
   return PSPACE_OK;
@@ -455,13 +504,24 @@ int ps_expand(const pspace_ctx *c, int k0, int k1, long long q0, long long q1, i
       if ((ncols_d + cand[k] * 8 - 1) / (cand[k] * 8) == min_tiles) wn = cand[k];
     if (z && wn == 3) wn = 4;       // complex tiles hold whole (re,im) pairs: even WN
     if (z && wn == 1) wn = 2;
+    // stage rows KC: the candidate whose best factorisation loads the producers least (ties: the larger stage)
+#define PS_XF(WN_, Z_)                                                                                        \
+  {                                                                                                            \
+    const XFChoice a128 = plan_expand_f<XTile<4, WN_, Z_, 128>>(c, f.nk), a64 = plan_expand_f<XTile<4, WN_, Z_, 64>>(c, f.nk), \
+                   a32 = plan_expand_f<XTile<4, WN_, Z_, 32>>(c, f.nk);                                       \
+    if (a128.ds >= 0 && (a64.ds < 0 || a128.score <= a64.score) && (a32.ds < 0 || a128.score <= a32.score))    \
+      return launch_expand_f<XTile<4, WN_, Z_, 128>>(c, f, d_V, st);                                           \
+    if (a64.ds >= 0 && (a32.ds < 0 || a64.score <= a32.score)) return launch_expand_f<XTile<4, WN_, Z_, 64>>(c, f, d_V, st); \
+    return launch_expand_f<XTile<4, WN_, Z_, 32>>(c, f, d_V, st);                                              \
+  }
     switch (wn) {
-      case 6: return z ? launch_expand_f<XTile<4, 6, true>>(c, f, d_V, st) : launch_expand_f<XTile<4, 6, false>>(c, f, d_V, st);
-      case 4: return z ? launch_expand_f<XTile<4, 4, true>>(c, f, d_V, st) : launch_expand_f<XTile<4, 4, false>>(c, f, d_V, st);
-      case 3: return launch_expand_f<XTile<4, 3, false>>(c, f, d_V, st);
-      case 2: return z ? launch_expand_f<XTile<4, 2, true>>(c, f, d_V, st) : launch_expand_f<XTile<4, 2, false>>(c, f, d_V, st);
-      default: return launch_expand_f<XTile<4, 1, false>>(c, f, d_V, st);
+      case 6: if (z) PS_XF(6, true) else PS_XF(6, false)
+      case 4: if (z) PS_XF(4, true) else PS_XF(4, false)
+      case 3: PS_XF(3, false)
+      case 2: if (z) PS_XF(2, true) else PS_XF(2, false)
+      default: PS_XF(1, false)
     }
+#undef PS_XF
   }
   // panel path, in q-slabs of at most 1 GiB of panel
   const long long np_est = ((k1 - k0) + 1) & ~1;

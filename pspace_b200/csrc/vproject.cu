@@ -23,16 +23,21 @@
 //
 // Algorithmic work: 2*m FLOP per (q,k) (x4 complex), bytes 8*(Q*m + N*m).  Bound: FP64 tensor pipe (DMMA); the operand
 // generation adds 1 DMUL per m/8.. DMMAs on the shared FP64 datapath (about 4 % for m = 24).
+#ifndef PS_EXPERIMENT
+#define PS_EXPERIMENT 0
+#endif
 #include "ctx.h"
 #include "factored.cuh"
 #include <algorithm>
+#include <atomic>
 #include <stdio.h>
+#include <stdlib.h>
+#include <vector>
 
 namespace {
 using namespace psf;
 
-constexpr int VT = 384;        // 8 consumer warps + 4 producer warps
-constexpr int VNCW = 8, VNPT = 128;
+constexpr int VNPT = 128;      // producer threads (4 warps); consumer warps = RG*KG per tile type
 constexpr int VKQ = 64;        // quadrature points per pipeline stage
 
 struct VParams {
@@ -49,6 +54,8 @@ struct VParams {
   int stages, stage_bytes;     // pipeline ring (host-sized)
   int accumulate;
   unsigned zero;               // run-time 0 (stage-release dependency, see mbar_arrive)
+  unsigned dephase_ns;
+  long long *dbg;              // PS_EXPERIMENT 9: per-CTA cycle stamps
 };
 
 template <int WM_, int WN_, int RG_, int KG_, bool CPLX_> struct VTile {
@@ -59,12 +66,14 @@ template <int WM_, int WN_, int RG_, int KG_, bool CPLX_> struct VTile {
   static constexpr int LDB = BN + 4;          // == 4 or 12 (mod 16): conflict-free B fragments
   static constexpr int SP = BM + 4;           // == 4 (mod 16): conflict-free S reads (k = lane%4 -> consecutive tail points)
   static constexpr int B_BYTES = VKQ * LDB * 8;
-  static_assert(RG * KG == VNCW, "8 consumer warps");
+  static constexpr int NCW = RG * KG, NT = NCW * 32 + VNPT;     // consumer warps, threads per CTA
+  static constexpr int CREG = NCW <= 8 ? 216 : (NCW <= 12 ? 136 : 104);   // setmaxnreg of the consumers
+  static_assert(RG % 4 == 0 && KG >= 1 && KG <= 4, "row groups spread over the 4 sub-partitions");
   static_assert(LDB % 16 == 4 || LDB % 16 == 12, "B pitch");
   // fixed shared-memory header: S planes, row offsets, accumulator exchange
   __host__ __device__ static size_t s_bytes(int L) { return (size_t)W * L * SP * 8; }
   __host__ __device__ static size_t eo_bytes(int nvars) { return ((size_t)nvars * BM * 2 + 15) & ~(size_t)15; }
-  __host__ __device__ static size_t xchg_bytes() { return KG == 2 ? (size_t)RG * 32 * WM * WN * 2 * 8 : 0; }
+  __host__ __device__ static size_t xchg_bytes() { return (size_t)(KG - 1) * RG * 32 * WM * WN * 2 * 8; }
   __host__ __device__ static int stage_bytes(int npfx) { return (B_BYTES + W * npfx * SP * 8 + VKQ * 8 + 127) / 128 * 128; }
   __host__ __device__ static size_t tab_bytes(int tsz) { return tsz <= psf::TAB_SMEM_MAX ? (size_t)tsz * W * 8 : 0; }
   __host__ __device__ static size_t header_bytes(int L, int nvars, int tsz) {
@@ -97,11 +106,12 @@ struct SkWork {
 };
 
 template <class TL>
-__global__ void __launch_bounds__(VT, 1) k_project_vf(const __grid_constant__ VParams p, const __grid_constant__ CUtensorMap tmapB) {
+__global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant__ VParams p, const __grid_constant__ CUtensorMap tmapB) {
   constexpr int WM = TL::WM, WN = TL::WN, RG = TL::RG, KG = TL::KG, W = TL::W, BM = TL::BM, BN = TL::BN;
   constexpr int LDB = TL::LDB, SP = TL::SP;
   constexpr bool CPLX = TL::CPLX;
   constexpr bool PAIRED = CPLX && (WN % 2) == 0;
+  constexpr int VNCW = TL::NCW, VT = TL::NT;
 
   extern __shared__ __align__(1024) unsigned char smem[];
   double *S = reinterpret_cast<double *>(smem);                                             // [W][L][SP]
@@ -164,7 +174,7 @@ __global__ void __launch_bounds__(VT, 1) k_project_vf(const __grid_constant__ VP
       long long c_hi = -1;
       double cbr = 1.0, cbi = 0.0;
       for (int c = c0; c < c1; c++) {
-        mbar_wait(&empty[s], ph ^ 1u);
+        if (p.dephase_ns) mbar_wait_backoff(&empty[s], ph ^ 1u, p.dephase_ns); else mbar_wait(&empty[s], ph ^ 1u);
         unsigned char *st = ring + (size_t)s * p.stage_bytes;
         if (pt == 0) {
           mbar_arrive_expect_tx(&full[s], TL::B_BYTES);
@@ -208,7 +218,7 @@ __global__ void __launch_bounds__(VT, 1) k_project_vf(const __grid_constant__ VP
     }
   } else {
     // =========================== CONSUMERS ===============================================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(216));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(TL::CREG));
     const int rg = warp % RG, kg = warp / RG;
     const int g = lane >> 2, kl = lane & 3;
     const unsigned sgn = (g & 1) ? 0u : 0x80000000u;
@@ -219,6 +229,9 @@ __global__ void __launch_bounds__(VT, 1) k_project_vf(const __grid_constant__ VP
     };
     int s = 0, it = 0;
     unsigned ph = 0;
+#if PS_EXPERIMENT == 9
+    long long t_begin = clock64(), t_sfull = 0, t_fullwait = 0, t_loop = 0, n_mine = 0;
+#endif
     for (int sidx = 0; sidx < nseg; sidx++) {
       int tile, c0, c1, slot;
       wk.segment(gcta, sidx, tile, c0, c1, slot);
@@ -228,14 +241,28 @@ __global__ void __launch_bounds__(VT, 1) k_project_vf(const __grid_constant__ VP
       for (int a = 0; a < WM; a++)
 #pragma unroll
         for (int b = 0; b < WN; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+#if PS_EXPERIMENT == 9
+      long long ta = clock64();
+#endif
       mbar_wait(s_full, (unsigned)sidx & 1u);
+#if PS_EXPERIMENT == 9
+      long long tb = clock64();
+      t_sfull += tb - ta;
+#endif
       const double *Sr = S + rbase;
       const double *Si = S + (size_t)p.L * SP + rbase;
 
       for (int c = c0; c < c1; c++, it++) {
-        const bool mine = KG == 1 || (it & 1) == kg;
+        const bool mine = KG == 1 || (it % KG) == kg;
         if (mine) {
+#if PS_EXPERIMENT == 9
+          long long tw0 = clock64();
+#endif
           mbar_wait(&full[s], ph);
+#if PS_EXPERIMENT == 9
+          t_fullwait += clock64() - tw0;
+          n_mine++;
+#endif
           const unsigned char *st = ring + (size_t)s * p.stage_bytes;
           const double *bs = reinterpret_cast<const double *>(st) + g;
           const double *bs2 = reinterpret_cast<const double *>(st) + 2 * g;
@@ -246,12 +273,22 @@ __global__ void __launch_bounds__(VT, 1) k_project_vf(const __grid_constant__ VP
 #pragma unroll
           for (int ks = 0; ks < VKQ / 4; ks++) {
             const int k = ks * 4 + kl;
+#if PS_EXPERIMENT == 2 || PS_EXPERIMENT == 3
+            const int2 ix = make_int2(k * SP, 0);
+#else
             const int2 ix = idx[k];
+#endif
             double are[WM], aim[WM];
 #pragma unroll
             for (int a = 0; a < WM; a++) {
               const double sr = Sr[ix.x + a * 8], pr = Pr[ix.y + a * 8];
+#if PS_EXPERIMENT == 4 || PS_EXPERIMENT == 5
+              if (!CPLX) are[a] = (double)(a + ks);
+#elif PS_EXPERIMENT == 1 || PS_EXPERIMENT == 3
+              if (!CPLX) are[a] = sr;
+#else
               if (!CPLX) are[a] = sr * pr;
+#endif
               else {
                 const double si = Si[ix.x + a * 8], pi = Pi[ix.y + a * 8];
                 are[a] = sr * pr - si * pi;
@@ -269,7 +306,11 @@ __global__ void __launch_bounds__(VT, 1) k_project_vf(const __grid_constant__ VP
             } else {
 #pragma unroll
               for (int b = 0; b < WN; b++) {
+#if PS_EXPERIMENT == 5
+                bfr[b] = (double)(b + ks);
+#else
                 bfr[b] = bs[k * LDB + b * 8];
+#endif
                 if (CPLX) bsw[b] = flip_sign(bs[k * LDB + b * 8 + ((g & 1) ? -1 : 1)], sgn);
               }
             }
@@ -290,11 +331,14 @@ __global__ void __launch_bounds__(VT, 1) k_project_vf(const __grid_constant__ VP
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
 
+#if PS_EXPERIMENT == 9
+      t_loop += clock64() - tb;
+#endif
       // ---- end of segment -------------------------------------------------------------------------
-      if (KG == 2) {
-        // the two k-groups hold partial sums of the same tile: group 1 hands its accumulators to group 0
-        double *x = xchg + ((size_t)rg * 32 + lane) * (WM * WN * 2);
-        if (kg == 1) {
+      if (KG > 1) {
+        // the k-groups hold partial sums of the same tile: groups 1.. hand their accumulators to group 0 (added in group order)
+        if (kg > 0) {
+          double *x = xchg + (((size_t)(kg - 1) * RG + rg) * 32 + lane) * (WM * WN * 2);
 #pragma unroll
           for (int a = 0; a < WM; a++)
 #pragma unroll
@@ -303,15 +347,19 @@ __global__ void __launch_bounds__(VT, 1) k_project_vf(const __grid_constant__ VP
         asm volatile("bar.sync 1, %0;\n" ::"n"(VNCW * 32) : "memory");
         if (kg == 0) {
 #pragma unroll
-          for (int a = 0; a < WM; a++)
+          for (int k2 = 1; k2 < KG; k2++) {
+            const double *x = xchg + (((size_t)(k2 - 1) * RG + rg) * 32 + lane) * (WM * WN * 2);
 #pragma unroll
-            for (int b = 0; b < WN; b++) { acc[a][b][0] += x[(a * WN + b) * 2]; acc[a][b][1] += x[(a * WN + b) * 2 + 1]; }
+            for (int a = 0; a < WM; a++)
+#pragma unroll
+              for (int b = 0; b < WN; b++) { acc[a][b][0] += x[(a * WN + b) * 2]; acc[a][b][1] += x[(a * WN + b) * 2 + 1]; }
+          }
         }
         asm volatile("bar.sync 1, %0;\n" ::"n"(VNCW * 32) : "memory");
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);            // this warp no longer reads S of the segment
-      if (KG == 2 && kg == 1) continue;
+      if (KG > 1 && kg > 0) continue;
       if (slot >= 0) {
         double *wsp = p.sk_ws + ((size_t)gcta * 2 + slot) * (BM * BN);
 #pragma unroll
@@ -344,6 +392,12 @@ __global__ void __launch_bounds__(VT, 1) k_project_vf(const __grid_constant__ VP
         }
       }
     }
+#if PS_EXPERIMENT == 9
+    if (p.dbg && lane == 0 && (warp == 0 || warp == RG)) {
+      long long *d = p.dbg + ((size_t)blockIdx.x * 2 + (warp == 0 ? 0 : 1)) * 8;
+      d[0] = clock64() - t_begin; d[1] = t_sfull; d[2] = t_fullwait; d[3] = t_loop; d[4] = n_mine; d[5] = nseg;
+    }
+#endif
   }
 }
 
@@ -388,6 +442,9 @@ typedef VTile<3, 1, 4, 2, false> V96x8;
 typedef VTile<3, 3, 4, 2, false> V96x24;
 typedef VTile<3, 4, 4, 2, false> V96x32;
 typedef VTile<3, 6, 4, 2, false> V96x48;
+typedef VTile<3, 3, 4, 3, false> V96x24k3;
+typedef VTile<3, 3, 4, 4, false> V96x24k4;
+typedef VTile<2, 3, 8, 2, false> V128x24k2;
 typedef VTile<2, 2, 8, 1, true> ZV128x16;
 typedef VTile<2, 4, 8, 1, true> ZV128x32;
 typedef VTile<2, 6, 8, 1, true> ZV128x48;
@@ -396,7 +453,8 @@ typedef VTile<3, 4, 4, 2, true> ZV96x32;
 typedef VTile<3, 6, 4, 2, true> ZV96x48;
 const VVariant V_REAL[] = {{1, 128, 8, "128x8"}, {2, 128, 24, "128x24"}, {3, 128, 32, "128x32"}, {4, 128, 48, "128x48"},
                            {5, 96, 8, "96x8 (2 k-groups)"}, {6, 96, 24, "96x24 (2 k-groups)"}, {7, 96, 32, "96x32 (2 k-groups)"},
-                           {8, 96, 48, "96x48 (2 k-groups)"}};
+                           {8, 96, 48, "96x48 (2 k-groups)"}, {9, 96, 24, "96x24 (3 k-groups)"}, {10, 96, 24, "96x24 (4 k-groups)"},
+                           {11, 128, 24, "128x24 (2 k-groups)"}};
 const VVariant V_CPLX[] = {{1, 128, 16, "128x16"}, {2, 128, 32, "128x32"}, {3, 128, 48, "128x48"},
                            {4, 96, 16, "96x16 (2 k-groups)"}, {5, 96, 32, "96x32 (2 k-groups)"}, {6, 96, 48, "96x48 (2 k-groups)"}};
 
@@ -443,9 +501,30 @@ template <class TL> int launch_v(const pspace_ctx *c, VParams &p, const VPlan &p
     if (rc) return rc;
   }
   if (pl.smem > (size_t)227 * 1024) return ps_fail(PSPACE_EINVAL, "vector projection: %zu bytes of shared memory", pl.smem);
-  PS_CUDA(cudaFuncSetAttribute(k_project_vf<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  k_project_vf<TL><<<pl.grid, VT, pl.smem, st>>>(p, tmB);
+  static std::atomic<bool> attr_dev[64];        // per instantiation and device; setting it twice is harmless
+  if (!attr_dev[c->device & 63].load(std::memory_order_acquire)) {
+    PS_CUDA(cudaFuncSetAttribute(k_project_vf<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_dev[c->device & 63].store(true, std::memory_order_release);
+  }
+#if PS_EXPERIMENT == 9
+  cudaMalloc(&p.dbg, (size_t)pl.grid * 16 * 8);
+  cudaMemset(p.dbg, 0, (size_t)pl.grid * 16 * 8);
+#endif
+  k_project_vf<TL><<<pl.grid, TL::NT, pl.smem, st>>>(p, tmB);
   PS_LAUNCH_CHECK(c);
+#if PS_EXPERIMENT == 9
+  {
+    std::vector<long long> h((size_t)pl.grid * 16);
+    cudaMemcpy(h.data(), p.dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(p.dbg);
+    for (int w = 0; w < 2; w++) {
+      double a[6] = {0, 0, 0, 0, 0, 0}, mx = 0;
+      for (int g = 0; g < pl.grid; g++) { for (int i = 0; i < 6; i++) a[i] += (double)h[((size_t)g * 2 + w) * 8 + i] / pl.grid; mx = std::max(mx, (double)h[((size_t)g * 2 + w) * 8]); }
+      fprintf(stderr, "[dbg] warp-group %d: total %.0f (max %.0f) s_full wait %.0f  full waits %.0f  chunk loops %.0f  my chunks %.1f  segments %.2f  -> per chunk %.0f cycles, wait %.0f\n",
+              w, a[0], mx, a[1], a[2], a[3], a[4], a[5], (a[3]) / a[4], a[2] / a[4]);
+    }
+  }
+#endif
   if (pl.rem_tiles > 0) {
     const int split = std::max(1, std::min((TL::BM * TL::BN) / 256, (2 * pl.grid + pl.rem_tiles - 1) / pl.rem_tiles));
     k_vfixup<<<dim3(pl.rem_tiles, split), 256, 0, st>>>(p, pl.grid, TL::BM, TL::BN);
@@ -457,10 +536,10 @@ template <class TL> int launch_v(const pspace_ctx *c, VParams &p, const VPlan &p
 int plan_v(const pspace_ctx *c, const pspace_project_args *a, VPlan &pl) {
   const int ncols_d = a->ncols * c->width, nk = a->k1 - a->k0;
   const VVariant *vs = c->is_complex ? V_CPLX : V_REAL;
-  const int nv = c->is_complex ? 6 : 8;
+  const int nv = c->is_complex ? 6 : 8, nv_all = c->is_complex ? 6 : 11;
   int best = -1;
   if (a->variant > 0) {
-    for (int i = 0; i < nv; i++) if (vs[i].id == a->variant) best = i;
+    for (int i = 0; i < nv_all; i++) if (vs[i].id == a->variant) best = i;
     if (best < 0) return ps_fail(PSPACE_EINVAL, "unknown vector tile variant %d", a->variant);
   } else {
     // fewest column tiles first (every column tile regenerates the operand), then the least padded work
@@ -511,7 +590,8 @@ int ps_vproject(const pspace_ctx *c, const pspace_project_args *a, const double 
   p.k0 = a->k0; p.nk = a->k1 - a->k0; p.ncols_d = a->ncols * c->width; p.nvars = c->nvars; p.DP = c->DP; p.tsz = c->tsz;
   for (int d = 0; d < PSPACE_MAX_VARS; d++) { p.toff[d] = d < c->nvars ? c->toff[d] : 0; p.nq[d] = d < c->nvars ? c->nq[d] : 1; }
   p.tiles_r = pl.tiles_r; p.tiles_n = pl.tiles_n; p.nchunk = pl.nchunk;
-  p.accumulate = a->accumulate; p.zero = 0;
+  p.accumulate = a->accumulate; p.zero = 0; p.dbg = nullptr;
+  p.dephase_ns = getenv("PS_DEPHASE") ? atoi(getenv("PS_DEPHASE")) : 0;
   const VVariant &v = (c->is_complex ? V_CPLX : V_REAL)[pl.vi];
   const int key = (c->is_complex ? 100 : 0) + v.id;
 #define PS_VCASE(K, TL)                                                                              \
@@ -523,6 +603,7 @@ int ps_vproject(const pspace_ctx *c, const pspace_project_args *a, const double 
   switch (key) {
     PS_VCASE(1, V128x8) PS_VCASE(2, V128x24) PS_VCASE(3, V128x32) PS_VCASE(4, V128x48)
     PS_VCASE(5, V96x8) PS_VCASE(6, V96x24) PS_VCASE(7, V96x32) PS_VCASE(8, V96x48)
+    PS_VCASE(9, V96x24k3) PS_VCASE(10, V96x24k4) PS_VCASE(11, V128x24k2)
     PS_VCASE(101, ZV128x16) PS_VCASE(102, ZV128x32) PS_VCASE(103, ZV128x48)
     PS_VCASE(104, ZV96x16) PS_VCASE(105, ZV96x32) PS_VCASE(106, ZV96x48)
     default: rc = ps_fail(PSPACE_EINVAL, "no vector kernel for key %d", key);

@@ -16,10 +16,11 @@ V = torch.randn((c.N, w.m), dtype=torch.float64, device="cuda").to(tdt)
 f = torch.randn((c.Q, w.m), dtype=torch.float64, device="cuda").to(tdt)
 U = torch.empty((c.Q, w.m), dtype=tdt, device="cuda")
 F = torch.empty((c.N, w.m), dtype=tdt, device="cuda")
+variant = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 for r in range(2):
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     e[0].record()
-    c.projectVector(f, out=F)
+    c.projectVector(f, out=F, variant=variant)
     e[1].record()
     c.evaluateExpansion(V, out=U)
     e[2].record()
