@@ -13,7 +13,10 @@
  * 1 or 2 doubles per scalar accordingly.
  *
  * Memory: arguments named d_* are DEVICE pointers owned by the caller; h_* are HOST pointers.
- * Streams: `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ * Streams: `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls on one context may use
+ * different streams: context-owned scratch (the basis panels of the matrix projection) is ordered across streams with
+ * events.  The HOST side of a context is not re-entrant: one thread at a time per context (entry points that change
+ * context state take a non-const `pspace_ctx *`).
  * Errors: every function returns PSPACE_OK (0) or a negative PSPACE_E* code; pspace_cuda_last_error()
  * returns a thread-local message.  There is NO CPU fallback: without a usable CUDA device the calls
  * fail with PSPACE_ECUDA.
@@ -131,14 +134,14 @@ typedef struct {
 } pspace_project_args;
 
 size_t pspace_cuda_project_workspace(const pspace_ctx *ctx, int is_matrix, const pspace_project_args *a);
-int pspace_cuda_project_vector(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_f,
+int pspace_cuda_project_vector(pspace_ctx *ctx, const pspace_project_args *a, const double *d_f,
                                double *d_F, void *d_workspace, size_t workspace_bytes, void *stream);
-int pspace_cuda_project_matrix(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_J,
+int pspace_cuda_project_matrix(pspace_ctx *ctx, const pspace_project_args *a, const double *d_J,
                                double *d_C, void *d_workspace, size_t workspace_bytes, void *stream);
 /* Many elements sharing one container (BASELINE.json configs[2]: "24x24 element Jacobians over 10k elements"): element e
  * reads d_J + e*j_elem_stride and writes d_C + e*c_elem_stride (strides in scalars); same window / q-range / workspace
  * for all.  The basis panels are built for the first element and reused. */
-int pspace_cuda_project_matrix_batched(const pspace_ctx *ctx, const pspace_project_args *a, int nelem, const double *d_J,
+int pspace_cuda_project_matrix_batched(pspace_ctx *ctx, const pspace_project_args *a, int nelem, const double *d_J,
                                        long long j_elem_stride, double *d_C, long long c_elem_stride, void *d_workspace,
                                        size_t workspace_bytes, void *stream);
 /* Host-buffer forms (the call a host-side user of the reference makes: pageable or pinned host
@@ -162,7 +165,7 @@ int pspace_cuda_project_matrix_hostin(pspace_ctx *ctx, const pspace_project_args
  * into this process).  pspace_cuda_peer_layout gives the receive-buffer size in doubles.  Restrictions: matrix mode,
  * no mask / symmetric / accumulate, even number of real columns (TMA path). */
 int pspace_cuda_peer_layout(const pspace_ctx *ctx, const pspace_project_args *a, int world, long long *recv_doubles);
-int pspace_cuda_project_matrix_peer(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_J,
+int pspace_cuda_project_matrix_peer(pspace_ctx *ctx, const pspace_project_args *a, const double *d_J,
                                     double *const *peer_recv, int world, int rank, void *d_workspace,
                                     size_t workspace_bytes, void *stream);
 int pspace_cuda_peer_reduce_gather(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_recv_local,
@@ -173,7 +176,7 @@ int pspace_cuda_peer_reduce_gather(const pspace_ctx *ctx, const pspace_project_a
  * scalars, row-major.  Replaces getDeterministicStates / getDeterministicAdjoint of the reference caller
  * (examples/stacs/cpp/TACSStochasticElement.cpp:53-120; pspace/core.py:788-792), which recompute it with N calls
  * of basis(k,zq) per node inside every (i,j,q) iteration. */
-int pspace_cuda_evaluate_expansion(const pspace_ctx *ctx, int k0, int k1, long long q0, long long q1, int ncols,
+int pspace_cuda_evaluate_expansion(pspace_ctx *ctx, int k0, int k1, long long q0, long long q1, int ncols,
                                    int accumulate, const double *d_V, double *d_U, void *stream);
 
 /* ---- (f2) TACS-interleaved layouts and the basis-pair sparsity filter (pure index work, bit-exact) ---------------
@@ -201,6 +204,8 @@ int pspace_cuda_pair_mask(const pspace_ctx *ctx, const int *dmapf, unsigned char
 int pspace_cuda_moments(const pspace_ctx *ctx, long long q0, long long q1, int ncols, const double *d_f,
                         double *d_mean, double *d_second, double *d_var, void *stream);
 
+/* make the context's device current for the calling thread (the shims below allocate on the CURRENT device) */
+int pspace_cuda_activate(const pspace_ctx *ctx);
 /* CUDA-runtime shims so that host code built without CUDA headers can stage buffers (to_device: 1 = H2D, 0 = D2H) */
 int pspace_cuda_malloc(void **p, size_t bytes);
 int pspace_cuda_free(void *p);

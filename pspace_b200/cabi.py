@@ -64,6 +64,7 @@ SIGNATURES = {
     "pspace_cuda_project_vector_host": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp]),
     "pspace_cuda_project_matrix_host": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp]),
     "pspace_cuda_project_matrix_hostin": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp]),
+    "pspace_cuda_activate": (_i, [_vp]),
     "pspace_cuda_launch_count": (_ll, [_vp]),
     "pspace_cuda_set_option": (_i, [_vp, ctypes.c_char_p, _i]),
     "pspace_cuda_last_plan": (_i, [_vp, ctypes.c_char_p, _i]),

@@ -69,7 +69,10 @@ int pspace_cuda_destroy(pspace_ctx *c) {
   cudaSetDevice(c->device);
   cudaFree(c->d_deg); cudaFree(c->d_zp); cudaFree(c->d_yp); cudaFree(c->d_wp); cudaFree(c->d_T); cudaFree(c->d_Tw);
   cudaFree(c->d_qdig); cudaFree(c->d_W);
+  cudaDeviceSynchronize();
   cudaFree(c->panel_u.d); cudaFree(c->panel_w.d);
+  if (c->panel_u.ev) cudaEventDestroy(c->panel_u.ev);
+  if (c->panel_w.ev) cudaEventDestroy(c->panel_w.ev);
   cudaFree(c->d_scratch_in); cudaFree(c->d_scratch_out); cudaFree(c->d_scratch_ws);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->copy_stream) {
@@ -112,7 +115,12 @@ int pspace_cuda_initialize_basis(pspace_ctx *c, const int *pmax, void *stream) {
   PS_CUDA(cudaStreamSynchronize(st));
   c->basis_ready = true;
   c->invalidate_panels();
-  return ps_build_tables(c, st);
+  rc = ps_build_tables(c, st);
+  if (rc) return rc;
+  // complete on return, like initialize_quadrature: the host getters copy on the legacy stream, which does not order
+  // against non-blocking streams
+  PS_CUDA(cudaStreamSynchronize(st));
+  return PSPACE_OK;
 }
 
 int pspace_cuda_initialize_quadrature(pspace_ctx *c, const int *nqpts, void *stream) {
@@ -220,7 +228,7 @@ size_t pspace_cuda_project_workspace(const pspace_ctx *c, int is_matrix, const p
   return ps_project_workspace(c, is_matrix, a);
 }
 
-int pspace_cuda_project_vector(const pspace_ctx *c, const pspace_project_args *a, const double *d_f, double *d_F,
+int pspace_cuda_project_vector(pspace_ctx *c, const pspace_project_args *a, const double *d_f, double *d_F,
                                void *d_ws, size_t ws_bytes, void *stream) {
   if (!c || !a) return ps_fail(PSPACE_EINVAL, "null argument");
   if ((!d_f && a->q1 > a->q0) || (!d_F && a->k1 > a->k0)) return ps_fail(PSPACE_EINVAL, "null buffer for a non-empty range");
@@ -228,7 +236,7 @@ int pspace_cuda_project_vector(const pspace_ctx *c, const pspace_project_args *a
   return ps_project(c, 0, a, d_f, d_F, d_ws, ws_bytes, (cudaStream_t)stream);
 }
 
-int pspace_cuda_project_matrix(const pspace_ctx *c, const pspace_project_args *a, const double *d_J, double *d_C,
+int pspace_cuda_project_matrix(pspace_ctx *c, const pspace_project_args *a, const double *d_J, double *d_C,
                                void *d_ws, size_t ws_bytes, void *stream) {
   if (!c || !a) return ps_fail(PSPACE_EINVAL, "null argument");
   if ((!d_J && a->q1 > a->q0) || (!d_C && a->k1 > a->k0 && a->j1 > a->j0))
@@ -237,7 +245,7 @@ int pspace_cuda_project_matrix(const pspace_ctx *c, const pspace_project_args *a
   return ps_project(c, 1, a, d_J, d_C, d_ws, ws_bytes, (cudaStream_t)stream);
 }
 
-int pspace_cuda_evaluate_expansion(const pspace_ctx *c, int k0, int k1, long long q0, long long q1, int ncols,
+int pspace_cuda_evaluate_expansion(pspace_ctx *c, int k0, int k1, long long q0, long long q1, int ncols,
                                    int accumulate, const double *d_V, double *d_U, void *stream) {
   if (!c) return ps_fail(PSPACE_EINVAL, "null argument");
   if ((!d_V && k1 > k0) || (!d_U && q1 > q0)) return ps_fail(PSPACE_EINVAL, "null buffer for a non-empty range");
@@ -249,7 +257,7 @@ int pspace_cuda_peer_layout(const pspace_ctx *c, const pspace_project_args *a, i
   if (!c || !a || !recv_doubles) return ps_fail(PSPACE_EINVAL, "null argument");
   return ps_peer_layout(c, a, world, recv_doubles);
 }
-int pspace_cuda_project_matrix_peer(const pspace_ctx *c, const pspace_project_args *a, const double *d_J,
+int pspace_cuda_project_matrix_peer(pspace_ctx *c, const pspace_project_args *a, const double *d_J,
                                     double *const *peer_recv, int world, int rank, void *d_ws, size_t ws_bytes, void *stream) {
   if (!c || !a || !d_J || !peer_recv) return ps_fail(PSPACE_EINVAL, "null argument");
   if (world < 1 || world > PSPACE_MAX_PEERS || rank < 0 || rank >= world) return ps_fail(PSPACE_EINVAL, "world/rank");
@@ -267,13 +275,13 @@ int pspace_cuda_peer_reduce_gather(const pspace_ctx *c, const pspace_project_arg
   return ps_peer_reduce_gather(c, a, d_recv_local, peer_out, world, rank, (cudaStream_t)stream);
 }
 
-int pspace_cuda_project_matrix_batched(const pspace_ctx *c, const pspace_project_args *a, int nelem, const double *d_J,
+int pspace_cuda_project_matrix_batched(pspace_ctx *c, const pspace_project_args *a, int nelem, const double *d_J,
                                        long long j_elem_stride, double *d_C, long long c_elem_stride, void *d_ws,
                                        size_t ws_bytes, void *stream) {
   if (!c || !a || nelem < 0) return ps_fail(PSPACE_EINVAL, "bad argument");
   if (nelem > 0 && (!d_J || !d_C)) return ps_fail(PSPACE_EINVAL, "null buffer");
   PS_CUDA(cudaSetDevice(c->device));
-  pspace_ctx *mc = const_cast<pspace_ctx *>(c);
+  pspace_ctx *mc = c;
   const int saved = mc->panel_cache;
   int rc = PSPACE_OK;
   for (int e = 0; e < nelem && rc == PSPACE_OK; e++) {
@@ -376,6 +384,12 @@ int pspace_cuda_project_matrix_hostin(pspace_ctx *c, const pspace_project_args *
   int rc = project_hostin(c, 1, a, h_J, d_C);
   if (rc) return rc;
   PS_CUDA(cudaStreamSynchronize(c->own_stream));
+  return PSPACE_OK;
+}
+
+int pspace_cuda_activate(const pspace_ctx *c) {
+  if (!c) return ps_fail(PSPACE_EINVAL, "null argument");
+  PS_CUDA(cudaSetDevice(c->device));
   return PSPACE_OK;
 }
 

@@ -47,6 +47,11 @@ struct pspace_ctx {
     bool valid = false;
     int r0 = 0, nr = 0;
     long long q0 = 0, q1 = 0;
+    // stream ordering: `ev` is recorded after the last kernel that wrote or read the slot; a call on ANY stream waits
+    // on it before it reuses, rebuilds or frees the slot (calls may come from different streams; the host side of a
+    // context is for one thread at a time — see include/pspace_cuda.h)
+    cudaEvent_t ev = nullptr;
+    bool ev_pending = false;
   };
   PanelSlot panel_u, panel_w;
   void invalidate_panels() { panel_u.valid = panel_w.valid = false; }
@@ -115,6 +120,8 @@ size_t ps_vproject_workspace(const pspace_ctx *ctx, const pspace_project_args *a
 bool ps_vproject_usable(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_in);
 int ps_vproject(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_in, double *d_out, void *d_ws,
                 size_t ws_bytes, cudaStream_t st);
+// records that the kernels enqueued on `st` so far use the panel slots (project.cu)
+void ps_panels_mark_used(pspace_ctx *c, cudaStream_t st);
 int ps_peer_layout(const pspace_ctx *ctx, const pspace_project_args *a, int world, long long *recv_elems);
 int ps_peer_reduce_gather(const pspace_ctx *ctx, const pspace_project_args *a, const double *d_recv, double *const *peer_out,
                           int world, int rank, cudaStream_t st);

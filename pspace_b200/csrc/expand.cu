@@ -552,6 +552,7 @@ int ps_expand(const pspace_ctx *c, int k0, int k1, long long q0, long long q1, i
       default: rc = z ? launch_expand<1, true>(c, p, st) : launch_expand<1, false>(c, p, st); break;
     }
   }
+  ps_panels_mark_used(const_cast<pspace_ctx *>(c), st);
   const_cast<pspace_ctx *>(c)->plan = "expand: basis panel streamed (round-1 kernel)";
   return rc;
 }

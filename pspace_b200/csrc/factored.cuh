@@ -41,21 +41,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
       "PSF_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// producer-side wait: polls with a back-off so that the spinning warp does not compete with the consumers for issue
-// slots and for the shared-memory pipe (a stage stays busy for ~1000 cycles; the producers are far ahead)
-__device__ __forceinline__ void mbar_wait_backoff(unsigned long long *bar, unsigned parity, unsigned ns) {
-  unsigned done;
-  for (;;) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (done) break;
-    __nanosleep(ns);
-  }
-}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, unsigned long long *bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
                ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");

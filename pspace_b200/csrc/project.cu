@@ -971,8 +971,14 @@ int ensure_panel(pspace_ctx *c, bool weighted, int r0, int nr, long long q0, lon
   const long long nq = q1 - q0;
   *nr_pad = (nr + 1) & ~1;
   const size_t need = (size_t)W * nq * *nr_pad * 8;
+  // order this call after the last use of the slot on whatever stream that was
+  if (s.ev_pending) PS_CUDA(cudaStreamWaitEvent(st, s.ev, 0));
   if (need > s.bytes) {
-    if (s.d) { PS_CUDA(cudaStreamSynchronize(st)); PS_CUDA(cudaFree(s.d)); s.d = nullptr; s.bytes = 0; }
+    if (s.d) {
+      if (s.ev_pending) PS_CUDA(cudaEventSynchronize(s.ev));
+      PS_CUDA(cudaStreamSynchronize(st));
+      PS_CUDA(cudaFree(s.d)); s.d = nullptr; s.bytes = 0;
+    }
     s.valid = false;
     cudaError_t e = cudaMalloc(&s.d, need);
     if (e != cudaSuccess) return ps_fail(PSPACE_ENOMEM, "basis panel of %zu bytes: %s", need, cudaGetErrorString(e));
@@ -1116,6 +1122,7 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
       PS_LAUNCH_CHECK(c);
     }
     if (d_list) PS_CUDA(cudaFreeAsync(d_list, st));
+    ps_panels_mark_used(mc, st);
     mc->plan_kernel = "tma+mbarrier warp-specialised, persistent stream-K";
     mc->plan_chunk_pts = LY::KQW;
     return PSPACE_OK;
@@ -1254,6 +1261,15 @@ int make_plan(const pspace_ctx *c, int is_matrix, const pspace_project_args *a, 
   return PSPACE_OK;
 }
 }  // namespace
+
+void ps_panels_mark_used(pspace_ctx *c, cudaStream_t st) {
+  pspace_ctx::PanelSlot *slots[2] = {&c->panel_u, &c->panel_w};
+  for (pspace_ctx::PanelSlot *s : slots) {
+    if (!s->d) continue;
+    if (!s->ev && cudaEventCreateWithFlags(&s->ev, cudaEventDisableTiming) != cudaSuccess) { s->ev = nullptr; continue; }
+    if (cudaEventRecord(s->ev, st) == cudaSuccess) s->ev_pending = true;
+  }
+}
 
 int ps_make_tmap(CUtensorMap *tm, const double *base, int rank, const unsigned long long *dims,
                  const unsigned long long *strides_bytes, const unsigned *box) {

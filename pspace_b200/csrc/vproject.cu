@@ -23,16 +23,11 @@
 //
 // Algorithmic work: 2*m FLOP per (q,k) (x4 complex), bytes 8*(Q*m + N*m).  Bound: FP64 tensor pipe (DMMA); the operand
 // generation adds 1 DMUL per m/8.. DMMAs on the shared FP64 datapath (about 4 % for m = 24).
-#ifndef PS_EXPERIMENT
-#define PS_EXPERIMENT 0
-#endif
 #include "ctx.h"
 #include "factored.cuh"
 #include <algorithm>
 #include <atomic>
 #include <stdio.h>
-#include <stdlib.h>
-#include <vector>
 
 namespace {
 using namespace psf;
@@ -54,8 +49,6 @@ struct VParams {
   int stages, stage_bytes;     // pipeline ring (host-sized)
   int accumulate;
   unsigned zero;               // run-time 0 (stage-release dependency, see mbar_arrive)
-  unsigned dephase_ns;
-  long long *dbg;              // PS_EXPERIMENT 9: per-CTA cycle stamps
 };
 
 template <int WM_, int WN_, int RG_, int KG_, bool CPLX_> struct VTile {
@@ -174,7 +167,7 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
       long long c_hi = -1;
       double cbr = 1.0, cbi = 0.0;
       for (int c = c0; c < c1; c++) {
-        if (p.dephase_ns) mbar_wait_backoff(&empty[s], ph ^ 1u, p.dephase_ns); else mbar_wait(&empty[s], ph ^ 1u);
+        mbar_wait(&empty[s], ph ^ 1u);
         unsigned char *st = ring + (size_t)s * p.stage_bytes;
         if (pt == 0) {
           mbar_arrive_expect_tx(&full[s], TL::B_BYTES);
@@ -229,9 +222,6 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
     };
     int s = 0, it = 0;
     unsigned ph = 0;
-#if PS_EXPERIMENT == 9
-    long long t_begin = clock64(), t_sfull = 0, t_fullwait = 0, t_loop = 0, n_mine = 0;
-#endif
     for (int sidx = 0; sidx < nseg; sidx++) {
       int tile, c0, c1, slot;
       wk.segment(gcta, sidx, tile, c0, c1, slot);
@@ -241,28 +231,14 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
       for (int a = 0; a < WM; a++)
 #pragma unroll
         for (int b = 0; b < WN; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-#if PS_EXPERIMENT == 9
-      long long ta = clock64();
-#endif
       mbar_wait(s_full, (unsigned)sidx & 1u);
-#if PS_EXPERIMENT == 9
-      long long tb = clock64();
-      t_sfull += tb - ta;
-#endif
       const double *Sr = S + rbase;
       const double *Si = S + (size_t)p.L * SP + rbase;
 
       for (int c = c0; c < c1; c++, it++) {
         const bool mine = KG == 1 || (it % KG) == kg;
         if (mine) {
-#if PS_EXPERIMENT == 9
-          long long tw0 = clock64();
-#endif
           mbar_wait(&full[s], ph);
-#if PS_EXPERIMENT == 9
-          t_fullwait += clock64() - tw0;
-          n_mine++;
-#endif
           const unsigned char *st = ring + (size_t)s * p.stage_bytes;
           const double *bs = reinterpret_cast<const double *>(st) + g;
           const double *bs2 = reinterpret_cast<const double *>(st) + 2 * g;
@@ -273,22 +249,12 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
 #pragma unroll
           for (int ks = 0; ks < VKQ / 4; ks++) {
             const int k = ks * 4 + kl;
-#if PS_EXPERIMENT == 2 || PS_EXPERIMENT == 3
-            const int2 ix = make_int2(k * SP, 0);
-#else
             const int2 ix = idx[k];
-#endif
             double are[WM], aim[WM];
 #pragma unroll
             for (int a = 0; a < WM; a++) {
               const double sr = Sr[ix.x + a * 8], pr = Pr[ix.y + a * 8];
-#if PS_EXPERIMENT == 4 || PS_EXPERIMENT == 5
-              if (!CPLX) are[a] = (double)(a + ks);
-#elif PS_EXPERIMENT == 1 || PS_EXPERIMENT == 3
-              if (!CPLX) are[a] = sr;
-#else
               if (!CPLX) are[a] = sr * pr;
-#endif
               else {
                 const double si = Si[ix.x + a * 8], pi = Pi[ix.y + a * 8];
                 are[a] = sr * pr - si * pi;
@@ -306,11 +272,7 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
             } else {
 #pragma unroll
               for (int b = 0; b < WN; b++) {
-#if PS_EXPERIMENT == 5
-                bfr[b] = (double)(b + ks);
-#else
                 bfr[b] = bs[k * LDB + b * 8];
-#endif
                 if (CPLX) bsw[b] = flip_sign(bs[k * LDB + b * 8 + ((g & 1) ? -1 : 1)], sgn);
               }
             }
@@ -331,9 +293,6 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
 
-#if PS_EXPERIMENT == 9
-      t_loop += clock64() - tb;
-#endif
       // ---- end of segment -------------------------------------------------------------------------
       if (KG > 1) {
         // the k-groups hold partial sums of the same tile: groups 1.. hand their accumulators to group 0 (added in group order)
@@ -392,16 +351,13 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
         }
       }
     }
-#if PS_EXPERIMENT == 9
-    if (p.dbg && lane == 0 && (warp == 0 || warp == RG)) {
-      long long *d = p.dbg + ((size_t)blockIdx.x * 2 + (warp == 0 ? 0 : 1)) * 8;
-      d[0] = clock64() - t_begin; d[1] = t_sfull; d[2] = t_fullwait; d[3] = t_loop; d[4] = n_mine; d[5] = nseg;
-    }
-#endif
   }
 }
 
-// adds the stream-K pieces of each remainder tile in CTA order and stores the tile.  grid = (remainder tiles, slices)
+// Adds the stream-K pieces of each remainder tile and stores the tile.  grid = (remainder tiles, element slices); a block
+// owns 64 elements x 4 piece lanes: lane j adds the pieces j, j+4, j+8, ... in CTA order and the four partial sums are
+// combined as (s0 + s1) + (s2 + s3) — a fixed order, so the result is reproducible run to run.
+constexpr int VFX_ELEMS = 64;
 __global__ void __launch_bounds__(256) k_vfixup(const __grid_constant__ VParams p, int G, int BM, int BN) {
   const SkWork wk(G, p.tiles_r * p.tiles_n, p.nchunk);
   const int rt = blockIdx.x, tile = wk.nfull * G + rt;
@@ -409,26 +365,36 @@ __global__ void __launch_bounds__(256) k_vfixup(const __grid_constant__ VParams 
   const long long u0 = (long long)rt * wk.nchunk, u1 = u0 + wk.nchunk;
   __shared__ int s_src[1024];
   __shared__ int s_n;
+  __shared__ double part[4][VFX_ELEMS];
   if (threadIdx.x == 0) {
+    // first CTA whose range reaches past u0, then every CTA until the ranges leave the tile
+    int g = (int)((u0 * G) / (wk.rem_units > 0 ? wk.rem_units : 1));
+    while (g > 0 && wk.lo(g) > u0) g--;
+    while (g < G && wk.lo(g + 1) <= u0) g++;
     int n = 0;
-    for (int g = 0; g < G && n < 1024; g++) {
+    for (; g < G && n < 1024; g++) {
       const long long a0 = wk.lo(g), a1 = wk.lo(g + 1);
-      if (a1 <= u0 || a1 <= a0) continue;
       if (a0 >= u1) break;
+      if (a1 <= a0) continue;
       s_src[n++] = g * 2 + ((a0 / wk.nchunk == rt) ? 0 : 1);
     }
     s_n = n;
   }
   __syncthreads();
-  const int npieces = s_n;
-  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < BM * BN; e += gridDim.y * blockDim.x) {
+  const int npieces = s_n, el = threadIdx.x & (VFX_ELEMS - 1), pl = threadIdx.x / VFX_ELEMS;
+  const int e = blockIdx.y * VFX_ELEMS + el;
+  double sum = 0.0;
+  if (e < BM * BN)
+    for (int k = pl; k < npieces; k += 4) sum += p.sk_ws[(size_t)s_src[k] * ((size_t)BM * BN) + e];
+  part[pl][el] = sum;
+  __syncthreads();
+  if (pl == 0 && e < BM * BN) {
     const int r = tr * BM + e / BN, col = tn * BN + e % BN;
-    if (r >= p.nk || col >= p.ncols_d) continue;
-    double sum = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < npieces; k++) sum += p.sk_ws[(size_t)s_src[k] * ((size_t)BM * BN) + e];
-    double *dst = p.out + (size_t)r * p.ncols_d + col;
-    *dst = p.accumulate ? *dst + sum : sum;
+    if (r < p.nk && col < p.ncols_d) {
+      const double tot = (part[0][el] + part[1][el]) + (part[2][el] + part[3][el]);
+      double *dst = p.out + (size_t)r * p.ncols_d + col;
+      *dst = p.accumulate ? *dst + tot : tot;
+    }
   }
 }
 
@@ -506,28 +472,10 @@ template <class TL> int launch_v(const pspace_ctx *c, VParams &p, const VPlan &p
     PS_CUDA(cudaFuncSetAttribute(k_project_vf<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_dev[c->device & 63].store(true, std::memory_order_release);
   }
-#if PS_EXPERIMENT == 9
-  cudaMalloc(&p.dbg, (size_t)pl.grid * 16 * 8);
-  cudaMemset(p.dbg, 0, (size_t)pl.grid * 16 * 8);
-#endif
   k_project_vf<TL><<<pl.grid, TL::NT, pl.smem, st>>>(p, tmB);
   PS_LAUNCH_CHECK(c);
-#if PS_EXPERIMENT == 9
-  {
-    std::vector<long long> h((size_t)pl.grid * 16);
-    cudaMemcpy(h.data(), p.dbg, h.size() * 8, cudaMemcpyDeviceToHost);
-    cudaFree(p.dbg);
-    for (int w = 0; w < 2; w++) {
-      double a[6] = {0, 0, 0, 0, 0, 0}, mx = 0;
-      for (int g = 0; g < pl.grid; g++) { for (int i = 0; i < 6; i++) a[i] += (double)h[((size_t)g * 2 + w) * 8 + i] / pl.grid; mx = std::max(mx, (double)h[((size_t)g * 2 + w) * 8]); }
-      fprintf(stderr, "[dbg] warp-group %d: total %.0f (max %.0f) s_full wait %.0f  full waits %.0f  chunk loops %.0f  my chunks %.1f  segments %.2f  -> per chunk %.0f cycles, wait %.0f\n",
-              w, a[0], mx, a[1], a[2], a[3], a[4], a[5], (a[3]) / a[4], a[2] / a[4]);
-    }
-  }
-#endif
   if (pl.rem_tiles > 0) {
-    const int split = std::max(1, std::min((TL::BM * TL::BN) / 256, (2 * pl.grid + pl.rem_tiles - 1) / pl.rem_tiles));
-    k_vfixup<<<dim3(pl.rem_tiles, split), 256, 0, st>>>(p, pl.grid, TL::BM, TL::BN);
+    k_vfixup<<<dim3(pl.rem_tiles, (TL::BM * TL::BN + VFX_ELEMS - 1) / VFX_ELEMS), 256, 0, st>>>(p, pl.grid, TL::BM, TL::BN);
     PS_LAUNCH_CHECK(c);
   }
   return PSPACE_OK;
@@ -590,8 +538,7 @@ int ps_vproject(const pspace_ctx *c, const pspace_project_args *a, const double 
   p.k0 = a->k0; p.nk = a->k1 - a->k0; p.ncols_d = a->ncols * c->width; p.nvars = c->nvars; p.DP = c->DP; p.tsz = c->tsz;
   for (int d = 0; d < PSPACE_MAX_VARS; d++) { p.toff[d] = d < c->nvars ? c->toff[d] : 0; p.nq[d] = d < c->nvars ? c->nq[d] : 1; }
   p.tiles_r = pl.tiles_r; p.tiles_n = pl.tiles_n; p.nchunk = pl.nchunk;
-  p.accumulate = a->accumulate; p.zero = 0; p.dbg = nullptr;
-  p.dephase_ns = getenv("PS_DEPHASE") ? atoi(getenv("PS_DEPHASE")) : 0;
+  p.accumulate = a->accumulate; p.zero = 0;
   const VVariant &v = (c->is_complex ? V_CPLX : V_REAL)[pl.vi];
   const int key = (c->is_complex ? 100 : 0) + v.id;
 #define PS_VCASE(K, TL)                                                                              \

@@ -27,7 +27,14 @@ class FusedShardedProjector:
         self.i0, self.i1 = i0, (container.N if i1 is None else i1)
         self.j0, self.j1 = j0, (container.N if j1 is None else j1)
         self.ncols = ncols
-        self.q0, self.q1 = shard_bounds(container.Q, self.world)[self.rank]
+        bounds = shard_bounds(container.Q, self.world)
+        # every rank sees every rank's range (no communication needed): fail on ALL ranks together instead of letting
+        # the ranks with points block in the barrier while an empty one raises
+        empty = [r for r, (a, b) in enumerate(bounds) if b <= a]
+        if empty:
+            raise ValueError(f"fused projection: {container.Q} quadrature points leave rank(s) {empty} of {self.world} without a "
+                             "shard; use fewer ranks or the NCCL path (ShardedProjector handles empty shards)")
+        self.q0, self.q1 = bounds[self.rank]
         self.args = ProjectArgs(self.i0, self.i1, self.j0, self.j1, self.q0, self.q1, ncols, 0, 0, 0, None, 0)
         L = container.L
         n = ctypes.c_longlong()

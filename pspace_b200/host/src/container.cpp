@@ -29,9 +29,21 @@ ParameterContainer::ParameterContainer(int basis_type_, int quadrature_type_)
 
 ParameterContainer::~ParameterContainer() { releaseDevice(); }
 
+extern "C" {
+// tiny CUDA-runtime shims exported by libpspace_cuda.so so this translation unit needs no CUDA headers
+int pspace_cuda_malloc(void **p, size_t bytes);
+int pspace_cuda_free(void *p);
+int pspace_cuda_memcpy(void *dst, const void *src, size_t bytes, int to_device);
+}
+
 void ParameterContainer::releaseDevice() {
-  if (ctx) { pspace_cuda_destroy(ctx); ctx = 0; }
-  d_ws = 0; ws_bytes = 0;   // owned by the context's allocator scope below (freed there)
+  if (ctx) {
+    pspace_cuda_activate(ctx);
+    if (d_ws) pspace_cuda_free(d_ws);       // workspace of the device-pointer forms (allocated through the shim)
+    pspace_cuda_destroy(ctx);
+    ctx = 0;
+  }
+  d_ws = 0; ws_bytes = 0;
 }
 
 void ParameterContainer::addParameter(AbstractParameter *param) {
@@ -52,7 +64,9 @@ int ParameterContainer::getNumParameters() { return tnum_parameters; }
 int ParameterContainer::getNumQuadraturePoints() { return (int)tnum_quadrature_points; }
 
 void ParameterContainer::ensureContext() {
-  if (ctx) return;
+  // the shims (malloc / memcpy) act on the CURRENT device: select the context's device on every entry, so that a
+  // process that switches devices between calls (several containers / torch) stays on the right GPU
+  if (ctx) { PS_MUST(pspace_cuda_activate(ctx)); return; }
   const int nv = tnum_parameters;
   std::vector<int> kinds(nv), dmax(nv);
   std::vector<scalar> p1(nv), p2(nv);
@@ -148,13 +162,6 @@ void ParameterContainer::getBasisParamMaxDeg(int *pmax) {
 pspace_ctx *ParameterContainer::deviceContext() { ensureContext(); return ctx; }
 
 // ---- batched GPU entry points ------------------------------------------------------------------------------
-extern "C" {
-// tiny CUDA-runtime shims exported by libpspace_cuda.so so this translation unit needs no CUDA headers
-int pspace_cuda_malloc(void **p, size_t bytes);
-int pspace_cuda_free(void *p);
-int pspace_cuda_memcpy(void *dst, const void *src, size_t bytes, int to_device);
-}
-
 void ParameterContainer::evalBasis(int npts, const scalar *z, scalar *psi) {
   ensureContext();
   const size_t w = PSPACE_SCALAR_WIDTH;

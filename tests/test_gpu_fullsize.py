@@ -106,7 +106,25 @@ def test_cfg4_complex_window_vs_oracle():
     assert float((Cw - Cw.transpose(0, 1)).abs().max()) < 1e-12 * float(Cw.abs().max())
     # full vector projection (N = Q = 65536, m = 24) against the oracle on a few rows
     f = J[:, :24].contiguous()
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    free0 = torch.cuda.mem_get_info()[0]
     F = c.projectVector(f)
+    torch.cuda.synchronize()
+    # no basis panel (round 1: 68.7 GB for this call): the operand is formed in shared memory; scratch = stream-K partials
+    assert "factored" in c.lastPlan()
+    assert torch.cuda.max_memory_allocated() - base < (1 << 30)
+    assert free0 - torch.cuda.mem_get_info()[0] < (1 << 30)              # nothing allocated behind torch's back either
     refF = o.project_vector(np.ascontiguousarray(Jh[:, :24]), 12345, 12348)
     assert normwise(F[12345:12348].cpu().numpy(), refF) < 1e-12
+    # expansion evaluation over all 65 536 basis rows (K loop of 1024 stages), a few points against the oracle,
+    # and project(evaluate(V)) == V (orthonormal basis, exact quadrature)
+    V = fill_synthetic(c.N * 4 * 2, w.seed + 7).view(torch.complex128).reshape(c.N, 4)
+    U = c.evaluateExpansion(V)
+    assert "factored" in c.lastPlan()
+    refU = o.evaluate_expansion(V.cpu().numpy(), 0, c.N, 30000, 30003)
+    assert normwise(U[30000:30003].cpu().numpy(), refU) < 1e-12
+    back = c.projectVector(U)
+    assert float((back - V).abs().max()) < 1e-10 * float(V.abs().max()) * 100
     c.close()

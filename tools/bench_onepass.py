@@ -17,7 +17,8 @@ from pspace_b200 import device as D  # noqa: E402
 from pspace_b200 import workloads as WL  # noqa: E402
 
 
-def gpu_time(fn, reps=10, warm=3):
+def gpu_time(fn, reps=7, warm=3, inner=10):
+    """CUDA events around `inner` back-to-back calls (the GPU never idles waiting for the host), per call."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -25,10 +26,11 @@ def gpu_time(fn, reps=10, warm=3):
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(inner):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / inner)
     ts.sort()
     return ts[0], ts[len(ts) // 2]
 

@@ -1,9 +1,13 @@
 #!/usr/bin/env python3
-"""Secondary operations of the path, measured on one B200 against the HBM roofline with the CPU oracle timed beside
-them (bounded samples).  The headline (matrix projection) is bench.py; this covers SURVEY.md §8 rows a1-a8 and f1-f3.
+"""Secondary operations of the path, measured on one B200 against the roofline that binds each of them — HBM bandwidth
+for the integer / table / reduction kernels, the FP64 DMMA peak for the two one-pass GEMMs (a8 vector projection, f1
+expansion evaluation: 2*N*m FLOP per point against 8*m bytes) — with the CPU oracle timed beside them (bounded samples).
+The headline (matrix projection) is bench.py; this covers SURVEY.md §8 rows a1-a8 and f1-f3.
 
-    python tools/bench_ops.py [cfg] > profiles/r01_ops.json       (default cfg5)
-"""
+    python tools/bench_ops.py [cfg] > profiles/r02_ops_cfg5.jsonl       (default cfg5)
+
+Timing: CUDA events around `inner` back-to-back calls (the GPU never waits for the host between them), best of 5 after 2
+warm-ups, divided by `inner`."""
 import json
 import os
 import sys
@@ -19,7 +23,7 @@ from pspace_b200 import device as D  # noqa: E402
 from pspace_b200 import workloads as WL  # noqa: E402
 
 
-def gpu_time(fn, reps=5, warm=2):
+def gpu_time(fn, reps=5, warm=2, inner=1):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -27,10 +31,11 @@ def gpu_time(fn, reps=5, warm=2):
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(inner):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1))
+        best = min(best, e0.elapsed_time(e1) / inner)
     return best
 
 
@@ -50,10 +55,16 @@ def main():
     tdt = torch.complex128 if w.complex_ else torch.float64
     rows = []
 
-    def add(name, ms, bytes_, unit_count, unit, cpu_rate=None, cpu_note="", note=""):
-        rows.append({"op": name, "workload": w.name, "ms": ms, "algorithmic_bytes": bytes_, "achieved_gbs": bytes_ / ms * 1e-6,
-                     "hbm_peak_gbs": hbm, "frac_of_hbm": bytes_ / ms * 1e-6 / hbm, "rate": unit_count / (ms * 1e-3), "unit": unit,
-                     "cpu_rate": cpu_rate, "cpu_note": cpu_note, "note": note})
+    fp64 = D.fp64_peak(1, 300.0, 0)
+
+    def add(name, ms, bytes_, unit_count, unit, cpu_rate=None, cpu_note="", note="", flop=None):
+        r = {"op": name, "workload": w.name, "ms": ms, "algorithmic_bytes": bytes_, "achieved_gbs": bytes_ / ms * 1e-6,
+             "hbm_peak_gbs": hbm, "frac_of_hbm": bytes_ / ms * 1e-6 / hbm, "rate": unit_count / (ms * 1e-3), "unit": unit,
+             "cpu_rate": cpu_rate, "cpu_note": cpu_note, "note": note, "bound": "hbm", "frac": bytes_ / ms * 1e-6 / hbm}
+        if flop is not None:      # FP64-bound operator: the binding roofline is the DMMA peak measured in this run
+            r.update({"bound": "fp64 (DMMA)", "useful_flop": flop, "achieved_tflops": flop / ms * 1e-9, "fp64_peak_tflops": fp64,
+                      "frac": flop / ms * 1e-9 / fp64})
+        rows.append(r)
 
     # (a1) multi-index construction
     pmax = np.array([p[3] for p in w.params], dtype=np.intc)
@@ -75,41 +86,33 @@ def main():
     add("tensor_grid Z,Y,W (a3)", ms, 8.0 * wd * (2 * nv + 1) * qn, qn, "grid points/s", note="includes 3 torch allocations")
     # (a5) batched basis at grid points
     kq = min(Q, 1 << 18)
-    ms = gpu_time(lambda: c.evalBasisGrid(0, N, 0, kq))
+    ms = gpu_time(lambda: c.evalBasisGrid(0, N, 0, kq), inner=4)
     add("eval_basis_grid (a5)", ms, 8.0 * wd * N * kq, float(N) * kq, "basis values/s", note=f"{kq} points, all {N} basis rows")
-    # (f1) expansion evaluation
+    # (f1) expansion evaluation and (a8) vector projection: one-pass GEMMs with a generated operand; algorithmic bytes are
+    # the m columns read / written per point, the binding roofline is FP64 (2*N*m FLOP per point, x4 complex)
     V = torch.randn((N, m), dtype=torch.float64, device="cuda").to(tdt)
     U = torch.empty((Q, m), dtype=tdt, device="cuda")
-    ms = gpu_time(lambda: c.evaluateExpansion(V, out=U))
+    F = torch.empty((N, m), dtype=tdt, device="cuda")
+    flop = 2.0 * N * Q * m * (4 if w.complex_ else 1)
     qs = min(Q, 4096)
     Vh = V.cpu().numpy()
     t = time.perf_counter()
     o.evaluate_expansion(Vh, 0, N, 0, qs)
     dt = time.perf_counter() - t
-    add("evaluate_expansion (f1)", ms, 8.0 * wd * (2 * N * Q + m * Q), float(N) * Q, "(k,q) terms/s", float(N) * qs / dt,
-        f"oracle, 1 thread, first {qs} points", "bytes = basis panel written + read once, U written")
-    # (a8) vector projection
-    f = U
-    F = torch.empty((N, m), dtype=tdt, device="cuda")
-    ms = gpu_time(lambda: c.projectVector(f, out=F))
-    add("project_vector (a8)", ms, 8.0 * wd * (m * Q + 2 * N * Q), float(N) * Q, "(k,q) updates/s",
-        note="bytes = f read, weighted panel written + read")
-    # the same two calls inside a time-stepping loop (expand -> caller -> project, same ranges every step): the
-    # unweighted and the weighted panel each stay in their context slot, so a step only reads them
-    c.setOption("panel_cache", 1)
-    c.evaluateExpansion(V, out=U)
-    c.projectVector(f, out=F)
-
-    def step():
-        c.evaluateExpansion(V, out=U)
-        c.projectVector(f, out=F)
-
-    ms = gpu_time(step)
-    add("evaluate_expansion + project_vector, cached panels (f1+a8)", ms, 8.0 * wd * (2 * N * Q + 2 * m * Q), 2.0 * N * Q,
-        "(k,q) terms/s", note="one step of a loop that repeats its ranges: bytes = both panels read once, U written, f read")
-    c.setOption("panel_cache", 0)
+    for force_panel in (0, 1):
+        if force_panel and 8.0 * wd * N * Q > 16e9:
+            continue
+        c.setOption("force_panel", force_panel)
+        tag = " [round-1 panel kernels]" if force_panel else ""
+        ms = gpu_time(lambda: c.evaluateExpansion(V, out=U), inner=10)
+        add("evaluate_expansion (f1)" + tag, ms, 8.0 * wd * (m * Q + N * m), float(N) * Q, "(k,q) terms/s", float(N) * qs / dt,
+            f"oracle, 1 thread, first {qs} points", c.lastPlan(), flop=flop)
+        f = U
+        ms = gpu_time(lambda: c.projectVector(f, out=F), inner=10)
+        add("project_vector (a8)" + tag, ms, 8.0 * wd * (m * Q + N * m), float(N) * Q, "(k,q) updates/s", note=c.lastPlan(), flop=flop)
+    c.setOption("force_panel", 0)
     # (f3) moments
-    ms = gpu_time(lambda: c.moments(f))
+    ms = gpu_time(lambda: c.moments(f), inner=10)
     fh = f[:min(Q, 1 << 16)].cpu().numpy()
     t = time.perf_counter()
     o.moments(fh, 0, fh.shape[0])
