@@ -153,6 +153,28 @@ int pspace_cuda_project_matrix_host(pspace_ctx *ctx, const pspace_project_args *
  * double buffer, overlapping the upload of slab s+1 with the projection of slab s (option "slab_mb"). */
 int pspace_cuda_project_matrix_hostin(pspace_ctx *ctx, const pspace_project_args *a, const double *h_J, double *d_C);
 
+/* ---- (e) multi-GPU: q-sharded projection + ONE NCCL collective over the coefficient blocks ---------------------------
+ * Quadrature points shard across ranks (one process or thread per GPU); rank r projects q in [q0_r, q1_r) — d_J / d_f hold
+ * only those rows — into a full partial window, and the partial windows are summed by ncclAllReduce (every rank ends with
+ * the total in d_C) or by ncclReduceScatter over blocks of basis rows (rank r ends with rows [r*per, (r+1)*per) of the total;
+ * for large N^2 m^2 or row-sharded consumers).  `nccl_comm` is the caller's ncclComm_t (ncclCommInitRank under MPI, as the
+ * reference's drivers initialise MPI: examples/stacs/smd/projection.cpp:36-39, or ncclCommInitAll); NCCL is resolved at run
+ * time from the libnccl.so.2 already in the process, libpspace_cuda.so has no link-time dependency on it.  All calls are
+ * asynchronous on `stream`.  pspace_cuda_shard_bounds gives the q-range of a rank (boundaries on multiples of 32 points,
+ * the rule of pspace_b200/sharded.py); pspace_cuda_row_block the row block of the reduce-scatter (per = ceil(rows/world)).
+ * reduce_scatter buffers: d_C_partial [world*per][(j1-j0)][ncols] scalars (scratch: the rank's partial window, padded),
+ * d_C_rows [per][(j1-j0)][ncols] scalars (result). */
+int pspace_cuda_shard_bounds(long long Q, int world, int rank, long long *q0, long long *q1);
+int pspace_cuda_row_block(int rows, int world, int rank, int *r0, int *r1, int *rows_per_rank);
+int pspace_cuda_nccl_allreduce(double *d_buf, size_t count_doubles, void *nccl_comm, void *stream);
+int pspace_cuda_project_matrix_allreduce(pspace_ctx *ctx, const pspace_project_args *a, const double *d_J, double *d_C,
+                                         void *d_workspace, size_t workspace_bytes, void *nccl_comm, void *stream);
+int pspace_cuda_project_vector_allreduce(pspace_ctx *ctx, const pspace_project_args *a, const double *d_f, double *d_F,
+                                         void *d_workspace, size_t workspace_bytes, void *nccl_comm, void *stream);
+int pspace_cuda_project_matrix_reduce_scatter(pspace_ctx *ctx, const pspace_project_args *a, const double *d_J,
+                                              double *d_C_partial, double *d_C_rows, void *d_workspace,
+                                              size_t workspace_bytes, void *nccl_comm, void *stream);
+
 /* ---- fused multi-GPU projection: compute + reduce-scatter/all-gather over peer-mapped memory (NVLink) -----------------
  * Each rank projects its quadrature-point shard; instead of keeping a full partial C and calling a collective, every
  * finished partial TILE is pushed by the projection kernel's epilogue straight into the receive slot of the rank that

@@ -57,6 +57,12 @@ SIGNATURES = {
     "pspace_cuda_project_workspace": (_sz, [_vp, _i, ctypes.POINTER(ProjectArgs)]),
     "pspace_cuda_project_vector": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _vp, _sz, _vp]),
     "pspace_cuda_project_matrix": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _vp, _sz, _vp]),
+    "pspace_cuda_shard_bounds": (_i, [_ll, _i, _i, ctypes.POINTER(_ll), ctypes.POINTER(_ll)]),
+    "pspace_cuda_row_block": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    "pspace_cuda_nccl_allreduce": (_i, [_vp, _sz, _vp, _vp]),
+    "pspace_cuda_project_matrix_allreduce": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _vp, _sz, _vp, _vp]),
+    "pspace_cuda_project_vector_allreduce": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _vp, _sz, _vp, _vp]),
+    "pspace_cuda_project_matrix_reduce_scatter": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "pspace_cuda_peer_layout": (_i, [_vp, ctypes.POINTER(ProjectArgs), _i, ctypes.POINTER(_ll)]),
     "pspace_cuda_project_matrix_peer": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "pspace_cuda_peer_reduce_gather": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp, _i, _i, _vp]),

@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
+#include <vector>
 #include "ctx.h"
 
 static thread_local char g_err[512] = "";
@@ -321,24 +323,36 @@ static int project_hostin(pspace_ctx *c, int is_matrix, const pspace_project_arg
   const long long nq = a->q1 - a->q0;
   const size_t row_bytes = sizeof(double) * w * a->ncols;
   const size_t in_bytes = row_bytes * (size_t)nq;
-  const size_t target = c->slab_bytes > 0 ? (size_t)c->slab_bytes : ((size_t)384 << 20);
-  long long nslab = (long long)((in_bytes + target - 1) / target);
-  nslab = nslab < 1 ? 1 : (nslab > 64 ? 64 : nslab);
-  long long slab_rows = (nq + nslab - 1) / nslab;
-  slab_rows = (slab_rows + 31) / 32 * 32;                       // keep every K-chunk of a slab full
-  if (slab_rows < 32) slab_rows = 32;
-  nslab = nq > 0 ? (nq + slab_rows - 1) / slab_rows : 0;
+  const size_t target = c->slab_bytes != 0 ? (size_t)(c->slab_bytes < 0 ? -c->slab_bytes : c->slab_bytes) : ((size_t)384 << 20);
+  // slab sizes: the first upload is the only one not hidden behind a projection, so the slabs START small (1/16 of the
+  // target) and double up to the target — the exposed copy shrinks 16x, the later slabs keep the kernel's stream-K waves long
+  long long max_rows = (long long)((target + row_bytes - 1) / (row_bytes ? row_bytes : 1));
+  max_rows = (max_rows + 63) / 64 * 64;                          // keep every 64-point stage of a slab full
+  if (max_rows < 64) max_rows = 64;
+  long long first_rows = c->slab_bytes < 0 ? max_rows : std::max<long long>(64, max_rows / 16 / 64 * 64);   // slab_mb < 0: equal slabs
+  std::vector<long long> starts;
+  {
+    long long r = 0, sz = first_rows;
+    while (r < nq && starts.size() < 4096) { starts.push_back(r); r += sz; sz = std::min(max_rows, sz * 2); }
+  }
+  const long long nslab = (long long)starts.size();
   int rc;
-  if ((rc = ensure(&c->d_scratch_in, &c->scratch_in_bytes, (nslab > 1 ? 2 : 1) * row_bytes * (size_t)slab_rows))) return rc;
+  if ((rc = ensure(&c->d_scratch_in, &c->scratch_in_bytes, (nslab > 1 ? 2 : 1) * row_bytes * (size_t)std::min(max_rows, std::max(nq, 1LL))))) return rc;
   pspace_project_args as = *a;
-  as.q0 = a->q0; as.q1 = a->q0 + (nq < slab_rows ? nq : slab_rows);
-  const size_t ws = ps_project_workspace(c, is_matrix, &as);      // the first slab is the largest
+  size_t ws = 0;                                                  // workspace: the largest need over the slabs
+  for (long long s = 0; s < nslab; s++) {
+    as.q0 = a->q0 + starts[s];
+    as.q1 = a->q0 + (s + 1 < nslab ? starts[s + 1] : nq);
+    ws = std::max(ws, ps_project_workspace(c, is_matrix, &as));
+  }
+  if (nslab == 0) { as = *a; ws = ps_project_workspace(c, is_matrix, &as); }
   if ((rc = ensure(&c->d_scratch_ws, &c->scratch_ws_bytes, ws))) return rc;
   if (nslab == 0) return ps_project(c, is_matrix, a, nullptr, d_out, c->d_scratch_ws, ws, st);
+  const size_t buf_stride = row_bytes * (size_t)std::min(max_rows, std::max(nq, 1LL));
   for (long long s = 0; s < nslab; s++) {
     const int b = (int)(s & 1);
-    const long long r0 = s * slab_rows, r1 = (r0 + slab_rows < nq) ? r0 + slab_rows : nq;
-    double *buf = (double *)((unsigned char *)c->d_scratch_in + (size_t)b * row_bytes * (size_t)slab_rows);
+    const long long r0 = starts[s], r1 = s + 1 < nslab ? starts[s + 1] : nq;
+    double *buf = (double *)((unsigned char *)c->d_scratch_in + (size_t)b * buf_stride);
     if (s >= 2) PS_CUDA(cudaStreamWaitEvent(cs, c->ev_comp[b], 0));        // buffer b is free again
     PS_CUDA(cudaMemcpyAsync(buf, (const unsigned char *)h_in + (size_t)r0 * row_bytes, (size_t)(r1 - r0) * row_bytes,
                             cudaMemcpyHostToDevice, cs));
@@ -417,7 +431,7 @@ int pspace_cuda_set_option(pspace_ctx *c, const char *name, int value) {
   if (!c || !name) return ps_fail(PSPACE_EINVAL, "null argument");
   if (!strcmp(name, "force_generic")) { c->force_generic = value; return PSPACE_OK; }
   if (!strcmp(name, "force_panel")) { c->force_panel = value; return PSPACE_OK; }
-  if (!strcmp(name, "slab_mb")) { c->slab_bytes = (long long)value << 20; return PSPACE_OK; }
+  if (!strcmp(name, "slab_mb")) { c->slab_bytes = value < 0 ? -((long long)(-value) << 20) : ((long long)value << 20); return PSPACE_OK; }
   if (!strcmp(name, "panel_cache")) { c->panel_cache = value; c->invalidate_panels(); return PSPACE_OK; }
   return ps_fail(PSPACE_EINVAL, "unknown option %s", name);
 }

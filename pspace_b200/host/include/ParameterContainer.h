@@ -64,6 +64,9 @@ class ParameterContainer {
   int projectMatrixDevice(int m2, const scalar *d_J, scalar *d_C, int i0, int i1, int j0, int j1, long long q0,
                           long long q1, void *stream);
   pspace_ctx *deviceContext();                  // for direct use of include/pspace_cuda.h
+  // GPU of this container (default: $PSPACE_DEVICE, else $LOCAL_RANK, else 0); call before initialize*().  One process
+  // per GPU needs nothing; a process that drives several GPUs from threads gives each thread's container its device.
+  void setDevice(int device);
 
  private:
   void ensureContext();
@@ -79,6 +82,7 @@ class ParameterContainer {
   std::vector<int> nqpts_;                      // 1-D rule sizes
   std::vector<std::vector<scalar> > zp, yp;     // mirrors of the device-built 1-D rules
   std::vector<scalar> W;                        // mirror of the device-built grid weights
+  int device_;                                  // -1 = from the environment
   void *d_ws;                                   // device scratch for the q-split of the device-pointer forms
   size_t ws_bytes;
 };

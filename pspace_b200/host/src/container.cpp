@@ -25,7 +25,7 @@ void die(const char *what, int rc) {
 
 ParameterContainer::ParameterContainer(int basis_type_, int quadrature_type_)
     : basis_type(basis_type_), quadrature_type(quadrature_type_), tnum_parameters(0), tnum_basis_terms(0),
-      tnum_quadrature_points(0), ctx(0), d_ws(0), ws_bytes(0) {}
+      tnum_quadrature_points(0), ctx(0), device_(-1), d_ws(0), ws_bytes(0) {}
 
 ParameterContainer::~ParameterContainer() { releaseDevice(); }
 
@@ -84,6 +84,7 @@ void ParameterContainer::ensureContext() {
   const char *env = getenv("PSPACE_DEVICE");      // one process per GPU: LOCAL_RANK selects the device
   if (!env) env = getenv("LOCAL_RANK");
   if (env) device = atoi(env);
+  if (device_ >= 0) device = device_;
   PS_MUST(pspace_cuda_create(&ctx, device, PSPACE_SCALAR_WIDTH == 2, nv, kinds.data(), (const double *)p1.data(),
                              (const double *)p2.data(), dmax.data(), basis_type));
 }
@@ -160,6 +161,10 @@ void ParameterContainer::getBasisParamMaxDeg(int *pmax) {
 }
 
 pspace_ctx *ParameterContainer::deviceContext() { ensureContext(); return ctx; }
+void ParameterContainer::setDevice(int device) {
+  if (device != device_) releaseDevice();
+  device_ = device;
+}
 
 // ---- batched GPU entry points ------------------------------------------------------------------------------
 void ParameterContainer::evalBasis(int npts, const scalar *z, scalar *psi) {

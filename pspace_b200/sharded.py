@@ -72,6 +72,50 @@ def combine(partial: torch.Tensor, mode: str = "allreduce", group=None):
     return mine, (r0, r1)
 
 
+class SharedPinnedOutput:
+    """One host buffer for the whole job: a POSIX shared-memory file mapped by every rank of the node and page-locked in
+    each process (cudaHostRegister), so that rank r's device-to-host copy lands directly in rows [r0, r1) of the result
+    every rank (and the caller) sees."""
+
+    def __init__(self, shape, dtype, group=None, tag="pspace_C"):
+        import os
+        self.shape, self.dtype = tuple(shape), dtype
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        name = [f"/dev/shm/{tag}_{os.getpid()}"] if rank == 0 else [None]
+        if world > 1:
+            dist.broadcast_object_list(name, src=0, group=group)
+        self.path, self.owner = name[0], rank == 0
+        n = 1
+        for d in self.shape:
+            n *= d
+        width = 2 if dtype.is_complex else 1
+        if self.owner:
+            with open(self.path, "wb") as f:
+                f.truncate(n * width * 8)
+        if world > 1:
+            dist.barrier(group=group)
+        flat = torch.from_file(self.path, shared=True, size=n * width, dtype=torch.float64)
+        self._flat = flat
+        rc = torch.cuda.cudart().cudaHostRegister(flat.data_ptr(), flat.numel() * 8, 0)
+        self.registered = int(rc) == 0 if not hasattr(rc, "value") else rc.value == 0
+        self.tensor = torch.view_as_complex(flat.view(*self.shape, 2)) if dtype.is_complex else flat.view(*self.shape)
+        if world > 1:
+            dist.barrier(group=group)
+
+    def close(self):
+        import os
+        try:
+            torch.cuda.cudart().cudaHostUnregister(self._flat.data_ptr())
+        except Exception:
+            pass
+        if self.owner:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
 class ShardedProjector:
     """Rank-local projector: owns a DeviceContainer and this rank's q-range."""
 
@@ -93,7 +137,7 @@ class ShardedProjector:
 
     def projectMatrixHost(self, J_local_host, out_host, i0=0, i1=None, j0=0, j1=None, dev_out=None):
         """End-to-end host form: this rank's J rows in (pinned) host memory -> slab-pipelined upload + projection ->
-        allreduce on the device -> the combined block in `out_host` (pinned).  Returns out_host."""
+        allreduce on the device -> the combined block in `out_host` (pinned, one full copy PER RANK).  Returns out_host."""
         i1 = self.c.N if i1 is None else i1
         j1 = self.c.N if j1 is None else j1
         m2 = J_local_host.shape[1]
@@ -104,6 +148,38 @@ class ShardedProjector:
         out_host.copy_(dev_out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out_host
+
+    def projectMatrixHostShared(self, J_local_host, out_shared, i0=0, i1=None, j0=0, j1=None):
+        """End-to-end host form for ONE result on the host: `out_shared` is a SharedPinnedOutput mapped by every rank.
+        This rank's J rows (pinned host) -> slab-pipelined upload + projection -> reduce-scatter over blocks of basis
+        rows on the device -> each rank copies ONLY its row block (1/world of C) into its slice of the shared host
+        buffer.  Round 1 let every rank read back the whole combined C (world x the bytes, contending for one host).
+        The result is complete on every rank when this returns (barrier)."""
+        i1 = self.c.N if i1 is None else i1
+        j1 = self.c.N if j1 is None else j1
+        m2 = J_local_host.shape[1]
+        rows, per = i1 - i0, (i1 - i0 + self.world - 1) // self.world
+        key = (rows, j1 - j0, m2)
+        if getattr(self, "_rs_key", None) != key:
+            # partial window padded to world equal row blocks (the pad rows stay zero), and my block of the total
+            self._rs_part = torch.zeros((per * self.world, j1 - j0, m2), dtype=self.c.t_dtype, device=self.c.device)
+            self._rs_mine = torch.empty((per, j1 - j0, m2), dtype=self.c.t_dtype, device=self.c.device)
+            self._rs_key = key
+        part, mine = self._rs_part, self._rs_mine
+        self.c.projectMatrixHostIn(J_local_host, part[:rows], i0, i1, j0, j1, q0=self.q0, q1=self.q1)
+        r0, r1 = min(rows, self.rank * per), min(rows, (self.rank + 1) * per)
+        if self.world > 1:
+            pr = torch.view_as_real(part) if part.is_complex() else part
+            mr = torch.view_as_real(mine) if mine.is_complex() else mine
+            dist.reduce_scatter_tensor(mr, pr, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            mine = part
+        if r1 > r0:
+            out_shared.tensor[r0:r1].copy_(mine[: r1 - r0], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        return out_shared.tensor, (r0, r1)
 
     def projectVector(self, f_local, k0=0, k1=None, out=None, mode="allreduce"):
         F = self.c.projectVector(f_local, k0, k1, q0=self.q0, q1=self.q1, out=out)

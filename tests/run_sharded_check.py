@@ -45,6 +45,23 @@ def main():
         Ch = torch.empty((40, o.N, m2), dtype=C.dtype).pin_memory()
         sp.projectMatrixHost(torch.from_numpy(np.ascontiguousarray(J[sp.q0:sp.q1])).pin_memory(), Ch, 0, 40, 0, o.N)
         F = sp.projectVector(Jl)
+        # the C-ABI collective entry point (what a C++ caller uses) on torch's own NCCL communicator, when torch exposes it
+        e_cabi = 0.0
+        comm_ptr = None
+        try:
+            comm_ptr = dist.distributed_c10d._get_default_group()._get_backend(torch.device("cuda"))._comm_ptr()
+        except Exception:
+            comm_ptr = None
+        Cc = None
+        if comm_ptr:
+            import ctypes
+            from pspace_b200.cabi import check
+            a = c._args(0, 40, 0, o.N, sp.q0, sp.q1, m2, False, 0, 0)
+            ws, need = c._workspace(1, a)
+            Cc = torch.empty((40, o.N, m2), dtype=C.dtype, device="cuda")
+            check(c.L.pspace_cuda_project_matrix_allreduce(c.h, ctypes.byref(a), Jl.data_ptr(), Cc.data_ptr(), ws.data_ptr() if ws is not None else None,
+                                                           need, ctypes.c_void_p(comm_ptr), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            torch.cuda.synchronize()
         from pspace_b200.fused import FusedShardedProjector
         fp = FusedShardedProjector(c, 0, 40, 0, o.N, ncols=m2)
         Cf = fp.projectMatrix(Jl).clone()
@@ -59,14 +76,17 @@ def main():
         e_fused = float(np.max(np.abs(Cf.cpu().numpy() - ref)) / den)
         if not torch.equal(Cf, Cf2):
             e_fused = 1.0
-        errs = torch.tensor([e_ar, e_rs, e_h, e_f, e_fused], dtype=torch.float64, device="cuda")
+        if Cc is not None:
+            e_cabi = float(np.max(np.abs(Cc.cpu().numpy() - ref)) / den)
+        errs = torch.tensor([e_ar, e_rs, e_h, e_f, e_fused, e_cabi], dtype=torch.float64, device="cuda")
         dist.all_reduce(errs, op=dist.ReduceOp.MAX)
         if rank == 0:
             e = [float(x) for x in errs]
             good = max(e) < 1e-12
             ok = ok and good
             print(json.dumps({"case": name, "world": world, "N": o.N, "Q": o.Q, "m2": m2, "allreduce_err": e[0], "reduce_scatter_err": e[1],
-                              "host_input_err": e[2], "vector_err": e[3], "fused_peer_err": e[4], "shards": [sp.q0, sp.q1], "pass": good}))
+                              "host_input_err": e[2], "vector_err": e[3], "fused_peer_err": e[4], "cabi_allreduce_err": e[5],
+                              "cabi_on_torch_comm": bool(comm_ptr), "shards": [sp.q0, sp.q1], "pass": good}))
         c.close()
     dist.destroy_process_group()
     return 0 if ok else 1
