@@ -226,6 +226,21 @@ int pspace_cuda_pair_mask(const pspace_ctx *ctx, const int *dmapf, unsigned char
 int pspace_cuda_moments(const pspace_ctx *ctx, long long q0, long long q1, int ncols, const double *d_f,
                         double *d_mean, double *d_second, double *d_var, void *stream);
 
+/* ---- (f4) adjoint-residual product ------------------------------------------------------------------------------
+ * TACSStochasticElement::addAdjResProduct (examples/stacs/cpp/TACSStochasticElement.cpp:548-637), three steps around the
+ * caller's deterministic element (m = nnodes*ndvpn local dofs; v, adj are TACS-interleaved stochastic vectors
+ * [nnodes*N*ndvpn] scalars on the device):
+ *   adjoint_states : d_UP[(q1-q0)][2m], columns [0,m) = deterministic states u_q, [m,2m) = deterministic adjoint psi_q
+ *                    (getDeterministicStates :84-120, getDeterministicAdjoint :53-82) — one expansion pass for both;
+ *   (caller)       : G[q][n] = g_n(psi_q, u_q, y_q), n < dvLen — the deterministic element's addAdjResProduct integrand;
+ *   adjoint_product: d_dfdx[n] (+)= scale * sum_{q in [q0,q1)} (w_q psi_0(z_q)) G[q][n]   (wt = basis(0,zq)*wq :590; the
+ *                    reference projects on basis index 0 only, :583).  h_scale points at ONE scalar on the host.
+ * A q-range = a rank's shard; the partial dfdx of the ranks add (pspace_cuda_nccl_allreduce). */
+int pspace_cuda_adjoint_states(pspace_ctx *ctx, int nnodes, int ndvpn, long long q0, long long q1, const double *d_v,
+                               const double *d_adj, double *d_UP, void *stream);
+int pspace_cuda_adjoint_product(pspace_ctx *ctx, int dvlen, const double *h_scale, long long q0, long long q1,
+                                const double *d_G, double *d_dfdx, int accumulate, void *stream);
+
 /* make the context's device current for the calling thread (the shims below allocate on the CURRENT device) */
 int pspace_cuda_activate(const pspace_ctx *ctx);
 /* CUDA-runtime shims so that host code built without CUDA headers can stage buffers (to_device: 1 = H2D, 0 = D2H) */

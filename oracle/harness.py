@@ -61,6 +61,10 @@ class _Api:
             fn = getattr(self.lib, "oracle_project_matrix_qrange" + suffix)
             fn.restype, fn.argtypes = None, [_vp, _i, _vp, _i, _i, _i, _i, _ll, _ll, _vp, _i]
             self.project_matrix_qrange = fn
+            fn = getattr(self.lib, "oracle_adj_res_product" + suffix)
+            fn.restype, fn.argtypes = None, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]
+            self.adj_res_product = fn
+            self.synthetic_adjres_element = ctypes.cast(getattr(self.lib, "oracle_synthetic_adjres_element" + suffix), _vp)
             fs = self.lib.oracle_fill_synthetic
             fs.restype, fs.argtypes = None, [_vp, _ll, ctypes.c_ulonglong, ctypes.c_ulonglong]
             self.fill_synthetic = fs
@@ -182,6 +186,20 @@ class CpuContainer:
         U = np.zeros((q1 - q0, V.shape[1]), dtype=self.dtype)
         self.api.evaluate_expansion(self.h, V.shape[1], _ptr(V), k0, k1, q0, q1, _ptr(U))
         return U
+
+    def adj_res_product(self, v, adj, nnodes, ndvpn, dvlen, scale=1.0, element=None, dfdx=None):
+        """(f4) TACSStochasticElement::addAdjResProduct (:548-637) over the TACS-interleaved stochastic state and adjoint
+        vectors v, adj [nnodes * N * ndvpn]; `element` = C callback of the deterministic element (default: the oracle's
+        synthetic one).  Adds into and returns dfdx[dvlen]."""
+        v = np.ascontiguousarray(v, dtype=self.dtype)
+        adj = np.ascontiguousarray(adj, dtype=self.dtype)
+        assert v.size == nnodes * self.N * ndvpn and adj.size == v.size
+        if dfdx is None:
+            dfdx = np.zeros(dvlen, dtype=self.dtype)
+        sc = np.array([scale], dtype=self.dtype)
+        self.api.adj_res_product(self.h, nnodes, ndvpn, dvlen, _ptr(sc), _ptr(v), _ptr(adj),
+                                 element if element is not None else self.api.synthetic_adjres_element, None, _ptr(dfdx))
+        return dfdx
 
     def moments(self, f, q0=0, q1=None):
         q1 = self.Q if q1 is None else q1

@@ -25,6 +25,11 @@ extern "C" {
 
 #define ORACLE_MAX_VARS 32
 
+/* the caller's deterministic element for (f4): adds scale * g(psi_q, u_q, y_q) into dfdx[dvlen]; every scalar array is
+ * double (real entry points) or interleaved (re,im) (_z entry points), scale points at one scalar */
+typedef void (*oracle_adjres_element)(void *user, const double *scale, const double *psi_q, const double *u_q,
+                                      const double *y_q, int m, int nvars, int dvlen, double *dfdx);
+
 /* kinds: 0 normal(mu,sigma)  1 uniform(a,b)  2 exponential(mu,beta) */
 #define ORACLE_DECL(SFX)                                                                              \
   void *oracle_create##SFX(int nvars, const int *kinds, const double *p1, const double *p2,           \
@@ -49,6 +54,12 @@ extern "C" {
                            double *second, double *var);                                               \
   void oracle_evaluate_expansion##SFX(void *h, int m, const double *V, int k0, int k1, long long q0,    \
                                       long long q1, double *U);                                        \
+  void oracle_adj_res_product##SFX(void *h, int nnodes, int ndvpn, int dvlen, const double *scale,      \
+                                   const double *v, const double *adj, oracle_adjres_element elem,      \
+                                   void *user, double *dfdx);                                           \
+  void oracle_synthetic_adjres_element##SFX(void *user, const double *scale, const double *psi_q,       \
+                                            const double *u_q, const double *y_q, int m, int nvars,      \
+                                            int dvlen, double *dfdx);                                    \
   /* q-range restricted variants used by the multi-GPU (sharded) parity tests */                      \
   void oracle_project_matrix_qrange##SFX(void *h, int m2, const double *J, int i0, int i1, int j0,    \
                                          int j1, long long q0, long long q1, double *C, int nthreads);

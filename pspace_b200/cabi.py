@@ -70,6 +70,8 @@ SIGNATURES = {
     "pspace_cuda_project_vector_host": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp]),
     "pspace_cuda_project_matrix_host": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp]),
     "pspace_cuda_project_matrix_hostin": (_i, [_vp, ctypes.POINTER(ProjectArgs), _vp, _vp]),
+    "pspace_cuda_adjoint_states": (_i, [_vp, _i, _i, _ll, _ll, _vp, _vp, _vp, _vp]),
+    "pspace_cuda_adjoint_product": (_i, [_vp, _i, _vp, _ll, _ll, _vp, _vp, _i, _vp]),
     "pspace_cuda_activate": (_i, [_vp]),
     "pspace_cuda_launch_count": (_ll, [_vp]),
     "pspace_cuda_set_option": (_i, [_vp, ctypes.c_char_p, _i]),

@@ -62,7 +62,6 @@ struct ProjParams {
   const int *tile_list;        // fast path with a mask: ids of the tiles that contain at least one kept pair ...
   const int *tile_count;       // ... and how many there are (device scalars: no host round trip)
   int symmetric;               // matrix mode, square window: compute pairs j >= i only and mirror the block to (j,i)
-  int zero;                    // always 0, but only known at run time (see the stage release in k_project_ws)
   // EPI_PEER: receive buffers of all ranks (peer-mapped), layout [src rank][owned pair tile][BM rows][ncols_pad]
   double *peer_recv[PSPACE_MAX_PEERS];
   int peer_world, peer_rank, peer_lp;      // ranks, my rank, pair tiles owned per rank (owner = pair tile / peer_lp)
@@ -607,6 +606,18 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
           const int s = it % STAGES;
           const unsigned n = (unsigned)(it / STAGES);
           mbar_wait(&empty[s], (n & 1u) ^ 1u);
+          // Stage-release ordering BY CONSTRUCTION.  A consumer warp arrives on empty[s] when it has ISSUED the last
+          // fragment load of the chunk in stage s — ptxas places the arrive right there, ahead of the DMMAs that consume
+          // the load — so that arrive alone does not prove the load has returned.  The refill therefore also waits for
+          // the release of the FOLLOWING chunk (it - STAGES + 1): a warp reaches that arrive only after it has left the
+          // spin-wait on the following chunk's `full` barrier, a branch that program order places after every DMMA of
+          // the chunk in stage s; a DMMA cannot issue before its operand registers are written, so by then every fragment
+          // load from stage s has returned.  Cost: the ring prefetches STAGES - 2 chunks ahead instead of STAGES - 1
+          // (measured: none), and the consumer loop — whose ptxas schedule is fragile — is untouched.
+          if (it >= STAGES) {
+            const int j = it - STAGES + 1;
+            mbar_wait(&empty[j % STAGES], (unsigned)(j / STAGES) & 1u);
+          }
           unsigned char *st = stage_base + (size_t)s * LY::STAGE_BYTES;
           const int row = c * KQ;                         // quadrature row relative to q0
           mbar_arrive_expect_tx(&full[s], LY::TX_BYTES);
@@ -702,7 +713,7 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
           }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
+      if (lane == 0) mbar_arrive(&empty[s]);      // see the producer: a stage is refilled one release LATER than this one
     }
 
     // ---- epilogue of this segment ----------------------------------------------------------------
@@ -1382,7 +1393,6 @@ int ps_project_ex(const pspace_ctx *c, int is_matrix, const pspace_project_args 
   p.out = d_out; p.slice_stride = 0; p.accumulate = a->accumulate; p.sk_ws = nullptr;
   p.mask = is_matrix ? a->d_pair_mask : nullptr; p.mask_ld = c->N; p.tile_list = nullptr; p.tile_count = nullptr;
   p.symmetric = 0;
-  p.zero = 0;
   p.peer_world = 0; p.peer_rank = 0; p.peer_lp = 1; p.peer_ncols_pad = 0;
   for (int w = 0; w < PSPACE_MAX_PEERS; w++) p.peer_recv[w] = nullptr;
   if (peer) {

@@ -252,6 +252,32 @@ class DeviceContainer:
         check(self.L.pspace_cuda_project_vector_host(self.h, ctypes.byref(a), fn.ctypes.data, on.ctypes.data))
         return out
 
+    def adjointStates(self, v, adj, nnodes, ndvpn, q0=0, q1=None, out=None):
+        """(f4 step 1) deterministic states and adjoint at the quadrature points from TACS-interleaved stochastic vectors
+        v, adj (device, [nnodes*N*ndvpn]): returns UP [q1-q0][2m], columns [0,m) = u_q, [m,2m) = psi_q."""
+        q1 = self.Q if q1 is None else q1
+        m = nnodes * ndvpn
+        assert v.is_cuda and adj.is_cuda and v.dtype == self.t_dtype and adj.dtype == self.t_dtype
+        assert v.is_contiguous() and adj.is_contiguous() and v.numel() == self.N * m and adj.numel() == self.N * m
+        if out is None:
+            out = torch.empty((q1 - q0, 2 * m), dtype=self.t_dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.L.pspace_cuda_adjoint_states(self.h, nnodes, ndvpn, q0, q1, v.data_ptr(), adj.data_ptr(), out.data_ptr(), _stream_ptr()))
+        return out
+
+    def adjointProduct(self, G, scale=1.0, q0=0, q1=None, out=None, accumulate=True):
+        """(f4 step 3) dfdx[n] (+)= scale * sum_q w_q psi_0(z_q) G[q][n]; G device [q1-q0][dvLen] from the caller's element."""
+        q1 = self.Q if q1 is None else q1
+        assert G.is_cuda and G.dtype == self.t_dtype and G.is_contiguous() and G.shape[0] == q1 - q0
+        dvlen = G.shape[1]
+        if out is None:
+            out = torch.zeros(dvlen, dtype=self.t_dtype, device=self.device)
+        sc = np.array([scale], dtype=self.np_dtype)
+        with torch.cuda.device(self.device):
+            check(self.L.pspace_cuda_adjoint_product(self.h, dvlen, cabi.np_ptr(sc), q0, q1, G.data_ptr(), out.data_ptr(), int(accumulate),
+                                                     _stream_ptr()))
+        return out
+
     def setOption(self, name, value):
         check(self.L.pspace_cuda_set_option(self.h, name.encode(), int(value)))
         return self

@@ -461,53 +461,86 @@ def test_panel_cache_slots_reuse_and_invalidate(cplx, force_panel):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
-def test_adjoint_residual_product_composition_vs_reference_loop(cplx):
-    """(f4) TACSStochasticElement::addAdjResProduct (TACSStochasticElement.cpp:548-637): for every quadrature point the
-    reference rebuilds the deterministic states u_q and adjoint psi_q from the TACS-interleaved stochastic vectors
-    (getDeterministicStates / getDeterministicAdjoint, :53-120) and adds wt*scale*g(psi_q, u_q, y_q) with
-    wt = basis(0, z_q) * w_q.  On the device this is gather -> two expansion evaluations -> the caller's product
-    (here a synthetic deterministic element) -> vector projection onto basis row 0.  The CPU side below is the
-    reference loop, quadrature point by quadrature point, over the oracle's basis()/quadrature() values."""
+def test_adjoint_residual_product_vs_oracle(cplx):
+    """(f4) TACSStochasticElement::addAdjResProduct (TACSStochasticElement.cpp:548-637) as a component: the device path
+    pspace_cuda_adjoint_states -> the caller's deterministic element (here the oracle's synthetic one, restated in torch)
+    -> pspace_cuda_adjoint_product, against the oracle's point-by-point restatement of the reference loop
+    (oracle_adj_res_product).  Also over two q-shards, whose partial dfdx add up (multi-GPU decomposition)."""
     from pspace_b200 import device as D
     rng = np.random.default_rng(77 + cplx)
     ps = [("normal", 0.3 + (1e-30j if cplx else 0), 1.2, 3), ("uniform", -1.0, 2.0, 2), ("exponential", 0.0, 0.5, 2)]
     o = H.CpuContainer(H.oracle_api(cplx), ps, 1).initialize()
     c = _dc(ps, 1, cplx).initialize()
-    N, Q, nv = o.N, o.Q, len(ps)
+    N, nv = o.N, len(ps)
     nnodes, ndvpn, dvlen, scale = 3, 2, 5, 0.75
-    m, nsvpn = nnodes * ndvpn, N * ndvpn
+    m = nnodes * ndvpn
 
     def rnd(n):
         a = rng.normal(size=n).astype(o.dtype)
         return a + 1j * rng.normal(size=n) if cplx else a
 
     v, adj = rnd(N * m), rnd(N * m)                 # TACS layout: [node][basis term][dof]
-    Zo, Yo, Wo = o.grid()
-    psi = o.basis_at(Zo)                            # [N][Q]
-
-    def element_product(pq, uq, yq):                # synthetic deterministic addAdjResProduct: dvLen values per point
-        return np.array([np.sum(pq * uq) * (1.0 + 0.1 * n) + yq[n % nv] * np.sum(uq) for n in range(dvlen)])
-
-    dfdx_ref = np.zeros(dvlen, dtype=o.dtype)
-    for q in range(Q):                              # :585-607
-        wt = psi[0, q] * Wo[q]
-        uq, pq = np.zeros(m, dtype=o.dtype), np.zeros(m, dtype=o.dtype)
-        for n in range(nnodes):                     # :84-120  u_q[n*ndvpn+d] = sum_k psi_k(z_q) v[n*nsvpn + k*ndvpn + d]
-            for k in range(N):
-                for d in range(ndvpn):
-                    uq[n * ndvpn + d] += psi[k, q] * v[n * nsvpn + k * ndvpn + d]
-                    pq[n * ndvpn + d] += psi[k, q] * adj[n * nsvpn + k * ndvpn + d]
-        dfdx_ref += wt * scale * element_product(pq, uq, Yo[q])
-
-    V = D.gather_vector_tacs(torch.from_numpy(v).cuda(), N, nnodes, ndvpn)
-    A = D.gather_vector_tacs(torch.from_numpy(adj).cuda(), N, nnodes, ndvpn)
-    U, P = c.evaluateExpansion(V), c.evaluateExpansion(A)               # [Q][m] each
+    ref = o.adj_res_product(v, adj, nnodes, ndvpn, dvlen, scale)
     _, Y, _ = c.grid()
-    su, spu = U.sum(dim=1), (P * U).sum(dim=1)
-    G = torch.stack([spu * (1.0 + 0.1 * n) + Y[:, n % nv] * su for n in range(dvlen)], dim=1).contiguous()
-    dfdx = scale * c.projectVector(G, 0, 1)[0]                          # basis row 0 only (:583)
-    assert normwise(dfdx.cpu().numpy(), dfdx_ref) < TOL
+
+    def element(UP, Yq):                            # the synthetic element's integrand, dvLen values per point
+        U, P = UP[:, :m], UP[:, m:]
+        spu, su = (P * U).sum(dim=1), U.sum(dim=1)
+        return torch.stack([spu * (1.0 + 0.1 * n) + Yq[:, n % nv] * su for n in range(dvlen)], dim=1).contiguous()
+
+    vd, ad = torch.from_numpy(v).cuda(), torch.from_numpy(adj).cuda()
+    UP = c.adjointStates(vd, ad, nnodes, ndvpn)
+    # the two halves are the plain expansions of the gathered vectors
+    assert normwise(UP[:, :m].cpu().numpy(), c.evaluateExpansion(D.gather_vector_tacs(vd, N, nnodes, ndvpn)).cpu().numpy()) < 1e-15
+    dfdx = c.adjointProduct(element(UP, Y), scale)
+    assert normwise(dfdx.cpu().numpy(), ref) < TOL
+    # accumulate semantics (the reference adds into dfdx) and q-shards
+    twice = c.adjointProduct(element(UP, Y), scale, out=dfdx.clone(), accumulate=True)
+    assert normwise(twice.cpu().numpy(), 2 * ref) < TOL
+    qs = c.Q // 3 + 1
+    part = c.adjointProduct(element(c.adjointStates(vd, ad, nnodes, ndvpn, 0, qs), Y[:qs]), scale, 0, qs)
+    part = c.adjointProduct(element(c.adjointStates(vd, ad, nnodes, ndvpn, qs, c.Q), Y[qs:]), scale, qs, c.Q, out=part, accumulate=True)
+    assert normwise(part.cpu().numpy(), ref) < TOL
     c.close()
+
+
+def test_complex_step_verifies_the_adjoint_product():
+    """The reference's verification flow (examples/stacs/smd/projection.cpp:228-236: RealPart(deriv) - ImagPart(f)/1e-30):
+    the USE_COMPLEX build carries a 1e-30j perturbation of a distribution parameter through rules, grid, expansion
+    evaluation, the element and the weighted reduction; Im(E[F])/1e-30 must equal the REAL build's adjoint-product
+    projection of dF/dmu.  F(y; u, psi) = (psi.u) y_0^2 + sum(u) y_0 y_1, y_0 = mu_0 + sigma_0 z  =>  dF/dmu_0 =
+    2 (psi.u) y_0 + sum(u) y_1 (u_q, psi_q do not depend on mu_0: the expansion lives in the standard variables z)."""
+    rng = np.random.default_rng(99)
+    h = 1e-30
+    nnodes, ndvpn = 2, 3
+    m = nnodes * ndvpn
+
+    def params(cplx):
+        return [("normal", 0.8 + (1j * h if cplx else 0.0), 0.35, 3), ("uniform", -0.5, 1.5, 3), ("exponential", 0.2, 0.6, 2)]
+
+    cr = _dc(params(False), 1, False).initialize()
+    cz = _dc(params(True), 1, True).initialize()
+    N = cr.N
+    v, adj = rng.normal(size=N * m), rng.normal(size=N * m)
+    # real build: adjoint-product projection of the derivative integrand
+    UP = cr.adjointStates(torch.from_numpy(v).cuda(), torch.from_numpy(adj).cuda(), nnodes, ndvpn)
+    _, Y, _ = cr.grid()
+    U, P = UP[:, :m], UP[:, m:]
+    G = (2.0 * (P * U).sum(1) * Y[:, 0] + U.sum(1) * Y[:, 1])[:, None].contiguous()
+    deriv = float(cr.adjointProduct(G)[0])
+    # complex build: the function itself, perturbed parameter
+    UPz = cz.adjointStates(torch.from_numpy(v.astype(np.complex128)).cuda(), torch.from_numpy(adj.astype(np.complex128)).cuda(), nnodes, ndvpn)
+    _, Yz, _ = cz.grid()
+    Uz, Pz = UPz[:, :m], UPz[:, m:]
+    Fz = ((Pz * Uz).sum(1) * Yz[:, 0] ** 2 + Uz.sum(1) * Yz[:, 0] * Yz[:, 1])[:, None].contiguous()
+    mean = complex(cz.adjointProduct(Fz)[0])
+    cs = mean.imag / h
+    assert abs(cs - deriv) <= 1e-10 * abs(deriv), (cs, deriv)
+    # and the real part is the real build's mean of F
+    Fr = ((P * U).sum(1) * Y[:, 0] ** 2 + U.sum(1) * Y[:, 0] * Y[:, 1])[:, None].contiguous()
+    assert abs(mean.real - float(cr.adjointProduct(Fr)[0])) <= 1e-12 * abs(mean.real)
+    cr.close()
+    cz.close()
 
 
 @pytest.mark.parametrize("cplx", [False, True])
@@ -748,4 +781,49 @@ def test_error_paths_are_loud():
     c.initialize()
     with pytest.raises(PspaceCudaError):
         c.projectVector(torch.zeros((3, 1), dtype=torch.float64, device="cuda"), 0, 9, 0, 3)   # k1 > N
+    c.close()
+
+
+@pytest.mark.parametrize("mode", ["dense", "masked", "symmetric", "complex"])
+def test_stage_release_ordering_under_memory_pressure(mode):
+    """The TMA ring of k_project_ws refills a stage only after the consumers have released the chunk AFTER the one that
+    occupied it (project.cu, producer): every fragment load has provably returned by then.  Stress: 50 repetitions of
+    a multi-chunk, multi-segment projection while a second stream saturates HBM with large copies (the condition that
+    exposed round 1's hazard: a busy load/store path); every repetition must be bit-identical to the first, and the
+    first must match the oracle."""
+    rng = np.random.default_rng(7)
+    cplx = mode == "complex"
+    ps = [("normal", 0.3 + (1e-30j if cplx else 0), 1.2, 3), ("uniform", -1.0, 2.0, 3), ("exponential", 0.0, 0.5, 3),
+          ("normal", -1.0, 0.4, 3), ("uniform", 0.0, 1.0, 3), ("normal", 1.0, 0.3, 3)]          # Q = 4096: 64 (128) chunks per tile
+    o = H.CpuContainer(H.oracle_api(cplx), ps, 1).initialize()
+    c = _dc(ps, 1, cplx).initialize()
+    m2 = 96
+    J = rng.normal(size=(o.Q, m2)).astype(o.dtype)
+    if cplx:
+        J = J + 1j * rng.normal(size=J.shape)
+    Jd = torch.from_numpy(J).cuda()
+    kw = {}
+    if mode == "masked":
+        kw["mask"] = c.pairMask([2] * len(ps))
+    if mode == "symmetric":
+        kw["symmetric"] = True
+    first = c.projectMatrix(Jd, **kw).clone()
+    assert "tma" in c.lastPlan()
+    ref = o.project_matrix(J, 0, 12, 60, o.N, nthreads=8)
+    got = first[0:12, 60:].cpu().numpy()
+    if mode == "masked":
+        got = c.projectMatrix(Jd)[0:12, 60:].cpu().numpy()
+    assert normwise(got, ref) < TOL
+    side = torch.cuda.Stream()
+    big_a = torch.empty(1 << 28, dtype=torch.float64, device="cuda")        # 2 GiB each
+    big_b = torch.empty(1 << 28, dtype=torch.float64, device="cuda")
+    big_a.fill_(1.0)
+    torch.cuda.synchronize()
+    for rep in range(50):
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                big_b.copy_(big_a, non_blocking=True)                       # ~1.3 ms of HBM-saturating traffic beside each projection
+        C = c.projectMatrix(Jd, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(C, first), (mode, rep)
     c.close()
