@@ -134,3 +134,51 @@ def test_unchanged_reference_cython_wrapper_runs_on_this_library(tag):
         pytest.skip("oracle/_ref/dropin not built (tools/build_dropin.py needs /root/reference)")
     r = subprocess.run([sys.executable, "-c", DROPIN_SCRIPT, pkg, ROOT, tag], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "DROPIN-OK" in r.stdout, r.stdout + r.stderr
+
+
+ADDITIVE_SCRIPT = r'''
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+import pspace.PSPACE as uq             # the reference wrapper + the additive binding of integration/PSPACE_additive.*.inc
+from oracle import harness as H
+cplx = sys.argv[3] == "complex"
+ps = [("normal", 1.0 + (1e-30j if cplx else 0.0), 0.1, 3), ("uniform", 1.0, 2.0, 2), ("exponential", 1.0, 0.1, 2)]
+f = uq.PyParameterFactory()
+pc = uq.PyParameterContainer(1)
+pc.addParameter(f.createNormalParameter(mu=ps[0][1], sigma=0.1, dmax=3))
+pc.addParameter(f.createUniformParameter(a=1.0, b=2.0, dmax=2))
+pc.addParameter(f.createExponentialParameter(mu=1.0, beta=0.1, dmax=2))
+pc.initialize()
+o = H.CpuContainer(H.oracle_api(cplx), ps, 1).initialize()
+N, Q = pc.getNumBasisTerms(), pc.getNumQuadraturePoints()
+assert (N, Q) == (o.N, o.Q)
+rng = np.random.default_rng(3)
+def rnd(*shape):
+    a = rng.normal(size=shape).astype(o.dtype)
+    return a + 1j * rng.normal(size=shape) if cplx else a
+nw = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+J, fv, V = rnd(Q, 16), rnd(Q, 4), rnd(N, 4)
+C = pc.projectMatrix(J)
+assert C.shape == (N, N, 16) and nw(C, o.project_matrix(J, nthreads=4)) < 1e-12
+Cw = pc.projectMatrix(J, window=(2, 7, 0, N))
+assert nw(Cw, o.project_matrix(J, 2, 7, 0, N)) < 1e-12
+assert nw(pc.projectVector(fv), o.project_vector(fv)) < 1e-12
+U = pc.evaluateExpansion(V)
+assert U.shape == (Q, 4) and nw(U, o.evaluate_expansion(V)) < 1e-12
+Z, _, _ = o.grid()
+assert nw(pc.evalBasis(Z[:9]), o.basis_at(Z[:9])) < 1e-13
+print("ADDITIVE-OK")
+'''
+
+
+@pytest.mark.parametrize("tag", ["real", "complex"])
+def test_additive_cython_binding_reaches_the_gpu_projections(tag):
+    """The reference's PSPACE.pyx / PSPACE.pxd with the additive binding applied (integration/PSPACE_additive.{pxd,pyx}.inc,
+    the patch INTEGRATION.md carries; built by tools/build_dropin.py from a scratch copy): a user of the reference's own
+    wrapper calls projectMatrix / projectVector / evaluateExpansion / evalBasis and gets the GPU path, checked against
+    the oracle."""
+    pkg = os.path.join(ROOT, "oracle", "_ref", "dropin_additive", tag)
+    if not os.path.isdir(os.path.join(pkg, "pspace")) or not any(f.startswith("PSPACE") and f.endswith(".so") for f in os.listdir(os.path.join(pkg, "pspace"))):
+        pytest.skip("oracle/_ref/dropin_additive not built (tools/build_dropin.py needs /root/reference)")
+    r = subprocess.run([sys.executable, "-c", ADDITIVE_SCRIPT, pkg, ROOT, tag], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ADDITIVE-OK" in r.stdout, r.stdout + r.stderr

@@ -8,6 +8,10 @@ Outputs (build artefacts only, git-ignored, shipped to the GPU box with the snap
 plus, beside each, an __init__.py and a _pointer_utils.py written HERE (three lines each; the compiled wrapper
 imports `pspace._pointer_utils.ensure_scalar_pointer / ensure_int_pointer` at run time) — no reference source
 file is copied into the repo; the .pyx/.pxd are cythonized from a scratch copy under /tmp.
+A second pair, oracle/_ref/dropin_additive/{real,complex}, is the same wrapper with the ADDITIVE binding of
+integration/PSPACE_additive.{pxd,pyx}.inc applied to the scratch copy (five extern lines inserted into the cppclass
+block of PSPACE.pxd, four def methods appended to PyParameterContainer in PSPACE.pyx — what INTEGRATION.md shows as a
+patch): projectVector / projectMatrix / evaluateExpansion / evalBasis reach the GPU from the reference's own wrapper.
 Runs only where /root/reference exists (the build container).  tests/test_gpu_dropin.py loads the result.
 """
 import os
@@ -35,11 +39,27 @@ def ensure_int_pointer(values, dtype=np.intc):
 '''
 
 
-def build(complex_):
+PXD_ANCHOR = "        void initializeQuadrature(const int *nqpts)\n"
+
+
+def apply_additive(pkg):
+    """The additive binding: insert the extern lines after the last method of `cdef cppclass ParameterContainer`, append the
+    def methods to `cdef class PyParameterContainer` (the last class of PSPACE.pyx)."""
+    inc = os.path.join(ROOT, "integration")
+    pxd = open(os.path.join(pkg, "PSPACE.pxd")).read()
+    assert pxd.count(PXD_ANCHOR) == 1, "PSPACE.pxd changed: anchor for the additive externs not found"
+    pxd = pxd.replace(PXD_ANCHOR, PXD_ANCHOR + open(os.path.join(inc, "PSPACE_additive.pxd.inc")).read())
+    open(os.path.join(pkg, "PSPACE.pxd"), "w").write(pxd)
+    pyx = open(os.path.join(pkg, "PSPACE.pyx")).read()
+    assert pyx.rstrip().endswith("return"), "PSPACE.pyx changed: PyParameterContainer is expected to be the last class"
+    open(os.path.join(pkg, "PSPACE.pyx"), "w").write(pyx.rstrip("\n") + "\n" + open(os.path.join(inc, "PSPACE_additive.pyx.inc")).read())
+
+
+def build(complex_, additive=False):
     import numpy
     from Cython.Build import cythonize
     tag = "complex" if complex_ else "real"
-    out_pkg = os.path.join(ROOT, "oracle", "_ref", "dropin", tag, "pspace")
+    out_pkg = os.path.join(ROOT, "oracle", "_ref", "dropin_additive" if additive else "dropin", tag, "pspace")
     os.makedirs(out_pkg, exist_ok=True)
     libdir = os.path.join(ROOT, "pspace_b200", "lib", "complex" if complex_ else "")
     libdir = os.path.normpath(libdir)
@@ -48,6 +68,8 @@ def build(complex_):
         os.makedirs(pkg)
         for f in ("PSPACE.pyx", "PSPACE.pxd"):
             shutil.copy(os.path.join(REF, "pspace", f), pkg)          # scratch copy, never enters the repo
+        if additive:
+            apply_additive(pkg)
         open(os.path.join(pkg, "__init__.py"), "w").close()
         with open(os.path.join(pkg, "_config.pxi"), "w") as fh:
             fh.write(f"DEF USE_COMPLEX = {1 if complex_ else 0}\n")
@@ -85,6 +107,8 @@ def main():
         return 0
     build(False)
     build(True)
+    build(False, additive=True)
+    build(True, additive=True)
     return 0
 
 
