@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (one kernel launch, --set full --import-source on) as markdown for profiles/.
 
-usage: tools/ncu_summary.py gpurun_out/x.ncu-rep "title" > profiles/x.md
+usage: tools/ncu_summary.py gpurun_out/x.ncu-rep "title" [kernel-regex] > profiles/x.md
 """
 import csv
 import io
@@ -28,13 +28,18 @@ KEYS = [
 ]
 
 
+KERNEL = []
+
+
 def page(rep, which):
-    out = subprocess.run(["ncu", "-i", rep, "--page", which, "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", which, "--csv"] + KERNEL, capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
 def main():
     rep, title = sys.argv[1], sys.argv[2]
+    if len(sys.argv) > 3:                       # optional: regex selecting one kernel of a multi-kernel report
+        KERNEL.extend(["--kernel-name", "regex:" + sys.argv[3]])
     raw = page(rep, "raw")
     hdr, units, vals = raw[0], raw[1], raw[2]
     d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
