@@ -9,20 +9,27 @@
 //
 //   w_q psi_k(z_q) = P_k[q div L] * S_k[q mod L]     with the weighted 1-D tables Tw_d = w_d T_d
 //
+// and P is constant over a prefix block of L consecutive points, so it leaves the inner loop altogether:
+//
+//   F[k][c] = sum_blocks P_k[b] * G_b[k][c],      G_b[k][c] = sum_{t in block b} S_k[t] f[b*L + t][c]
+//
+//   * work is cut into CHUNKS that never cross a block: a block is split at multiples of 64 points inside the block
+//     (cfg5 / cfg4: L = 64, one chunk per block), the first and last block of the call's q-range are clipped to it;
 //   * S (rows of the CTA's row tile x L tail points) is written to shared memory once per work segment by the producer
-//     warps; P (rows x the <= npfx prefix blocks a 64-point stage touches) once per stage, next to the f tile that one
-//     elected producer thread fetches with TMA (cp.async.bulk.tensor, mbarrier expect_tx, zero-filled ragged edges);
-//   * consumer warps: A-fragment element = S * P (ONE DMUL, two shared-memory reads), feeding WN DMMA.8x8x4 each;
-//   * warp grid RG row groups x KG k-groups: with KG = 2 the two warps of an SM sub-partition take alternate stages
-//     (their chunk boundaries interleave by construction) and add their accumulators through shared memory at the end
-//     of a segment — this is what makes a 96-row tile possible (286 basis rows = 3 x 96 - 2, instead of 3 x 128 - 98);
-//   * work = (row tile, column tile, 64-point chunk) units cut into G equal contiguous ranges (stream-K, one persistent
-//     CTA per SM): full tiles are stored straight to F, partial ones go to a workspace and k_vfixup adds the pieces of
-//     each tile in CTA order (deterministic, no atomics);
+//     warps; per chunk they write ONE prefix value per row and a chunk descriptor, next to the f rows that one elected
+//     producer thread fetches with TMA (cp.async.bulk.tensor, mbarrier expect_tx, zero-filled ragged edges);
+//   * consumer warps: per chunk a fresh accumulator G; the DMMA A fragment is S itself (shared-memory reads at
+//     compile-time offsets from one base: no multiply, no index map), B = f; after the chunk acc += P * G
+//     (WM*WN*2 DFMA per lane and chunk instead of one DMUL per A element and k-step);
+//   * warp grid RG row groups x KG k-groups: with KG = 2 the two warps of an SM sub-partition take alternate chunks and add
+//     their accumulators through shared memory at the end of a segment — this is what makes a 96-row tile possible
+//     (286 basis rows = 3 x 96 - 2, instead of 3 x 128 - 98);
+//   * work = (row tile, column tile, chunk) units cut into G equal contiguous ranges (stream-K, one persistent CTA per
+//     SM): full tiles are stored straight to F, partial ones go to a workspace and k_vfixup adds the pieces of each tile
+//     in a fixed order (deterministic, no atomics);
 //   * a stage is released with an mbarrier arrive whose address depends on the stage's last fragment registers.
 //
-// Algorithmic work: 2*m FLOP per (q,k) (x4 complex), bytes 8*(Q*m + N*m).  Bound: FP64 tensor pipe (DMMA); the operand
-// generation adds 1 DMUL per m/8.. DMMAs on the shared FP64 datapath (about 4 % for m = 24).
+// Algorithmic work: 2*m FLOP per (q,k) (x4 complex), bytes 8*(Q*m + N*m).  Bound: FP64 tensor pipe (DMMA).
 #include "ctx.h"
 #include "factored.cuh"
 #include <algorithm>
@@ -44,7 +51,7 @@ struct VParams {
   long long q0, q1, Qtot;
   int k0, nk, ncols_d, nvars, DP, tsz;
   int toff[PSPACE_MAX_VARS], nq[PSPACE_MAX_VARS];
-  int dsplit, L, npfx;         // tail = variables [dsplit, nvars); L = prod of their rule sizes; prefix slots per stage
+  int dsplit, L, LP;           // tail = variables [dsplit, nvars); L = prod of their rule sizes; LP = S rows incl. zero pad
   int tiles_r, tiles_n, nchunk;
   int stages, stage_bytes;     // pipeline ring (host-sized)
   int accumulate;
@@ -67,7 +74,7 @@ template <int WM_, int WN_, int RG_, int KG_, bool CPLX_> struct VTile {
   __host__ __device__ static size_t s_bytes(int L) { return (size_t)W * L * SP * 8; }
   __host__ __device__ static size_t eo_bytes(int nvars) { return ((size_t)nvars * BM * 2 + 15) & ~(size_t)15; }
   __host__ __device__ static size_t xchg_bytes() { return (size_t)(KG - 1) * RG * 32 * WM * WN * 2 * 8; }
-  __host__ __device__ static int stage_bytes(int npfx) { return (B_BYTES + W * npfx * SP * 8 + VKQ * 8 + 127) / 128 * 128; }
+  __host__ __device__ static int stage_bytes() { return (B_BYTES + W * SP * 8 + 16 + 127) / 128 * 128; }
   __host__ __device__ static size_t tab_bytes(int tsz) { return tsz <= psf::TAB_SMEM_MAX ? (size_t)tsz * W * 8 : 0; }
   __host__ __device__ static size_t header_bytes(int L, int nvars, int tsz) {
     return (s_bytes(L) + eo_bytes(nvars) + xchg_bytes() + tab_bytes(tsz) + 127) / 128 * 128;
@@ -98,6 +105,30 @@ struct SkWork {
   }
 };
 
+// Chunks never cross a prefix block: block b of L points is cut at multiples of 64 inside the block (cpb chunks per
+// block); the first and the last block of the call's q-range are clipped to it.  Chunk c of the range -> block, tail range.
+struct ChunkMap {
+  long long q0, q1, b0, b1;
+  int L, cpb, r0, e1;
+  __host__ __device__ ChunkMap(long long q0_, long long q1_, int L_) : q0(q0_), q1(q1_), L(L_) {
+    cpb = (L + VKQ - 1) / VKQ;
+    b0 = q0 / L; r0 = (int)(q0 - b0 * L);
+    b1 = q1 > q0 ? (q1 - 1) / L : b0; e1 = q1 > q0 ? (int)((q1 - 1) - b1 * L) + 1 : r0;
+  }
+  __host__ __device__ long long nchunk() const { return q1 > q0 ? (b1 - b0 + 1) * cpb : 0; }
+  // tail range [tlo, thi) of sub-chunk j of block b (may be empty at the clipped ends).  Sub-chunks start at the block's
+  // first point INSIDE the range (r0 in the first block) and are 64 long, so only the last one of a block can have a
+  // length that is not a multiple of 4 — its last k-step then reads the zero pad of S (block end) or rows of f past the
+  // range, which TMA fills with zeros (clipped end); it never reaches into the next sub-chunk.
+  __host__ __device__ void range(long long b, int j, int &tlo, int &thi) const {
+    tlo = (b == b0 ? r0 : 0) + j * VKQ;
+    if (tlo > L) tlo = L;
+    thi = tlo + VKQ < L ? tlo + VKQ : L;
+    if (b == b1 && thi > e1) thi = e1;
+    if (thi < tlo) thi = tlo;
+  }
+};
+
 template <class TL>
 __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant__ VParams p, const __grid_constant__ CUtensorMap tmapB) {
   constexpr int WM = TL::WM, WN = TL::WN, RG = TL::RG, KG = TL::KG, W = TL::W, BM = TL::BM, BN = TL::BN;
@@ -107,19 +138,21 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
   constexpr int VNCW = TL::NCW, VT = TL::NT;
 
   extern __shared__ __align__(1024) unsigned char smem[];
-  double *S = reinterpret_cast<double *>(smem);                                             // [W][L][SP]
-  unsigned short *eo = reinterpret_cast<unsigned short *>(smem + TL::s_bytes(p.L));         // [nvars][BM]
-  double *xchg = reinterpret_cast<double *>(smem + TL::s_bytes(p.L) + TL::eo_bytes(p.nvars));
-  double *Ts = reinterpret_cast<double *>(smem + TL::s_bytes(p.L) + TL::eo_bytes(p.nvars) + TL::xchg_bytes());
-  unsigned char *ring = smem + TL::header_bytes(p.L, p.nvars, p.tsz);
+  const int LP = p.LP;                                                                     // S rows incl. the zero pad
+  double *S = reinterpret_cast<double *>(smem);                                             // [W][LP][SP]
+  unsigned short *eo = reinterpret_cast<unsigned short *>(smem + TL::s_bytes(LP));          // [nvars][BM]
+  double *xchg = reinterpret_cast<double *>(smem + TL::s_bytes(LP) + TL::eo_bytes(p.nvars));
+  double *Ts = reinterpret_cast<double *>(smem + TL::s_bytes(LP) + TL::eo_bytes(p.nvars) + TL::xchg_bytes());
+  unsigned char *ring = smem + TL::header_bytes(LP, p.nvars, p.tsz);
   const int STAGES = p.stages;
   unsigned long long *full = reinterpret_cast<unsigned long long *>(ring + (size_t)STAGES * p.stage_bytes);
   unsigned long long *empty = full + STAGES;
   unsigned long long *s_full = empty + STAGES, *s_free = s_full + 1;
-  const int P_OFF = TL::B_BYTES, IDX_OFF = TL::B_BYTES + W * p.npfx * SP * 8;
+  constexpr int P_OFF = TL::B_BYTES, D_OFF = TL::B_BYTES + W * SP * 8;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const SkWork wk(gridDim.x, p.tiles_r * p.tiles_n, p.nchunk);
+  const ChunkMap cm(p.q0, p.q1, p.L);
   const int gcta = blockIdx.x, nseg = wk.nseg(gcta);
 
   const bool tab_smem = p.tsz <= TAB_SMEM_MAX;
@@ -147,65 +180,59 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
       const int tn = tile % p.tiles_n, tr = tile / p.tiles_n;
       const int k = p.k0 + tr * BM + pt;
       const bool valid = pt < BM && k < p.k0 + p.nk;
-      // ---- per-segment: row offsets and the tail table S of this row tile ----
+      // ---- per segment: row offsets and the tail table S of this row tile (rows [L, LP) are the zero pad) ----
       if (sidx > 0) mbar_wait(s_free, (unsigned)(sidx - 1) & 1u);
       if (pt < BM) {
         for (int d = 0; d < p.nvars; d++)
           eo[d * BM + pt] = (unsigned short)(valid ? p.toff[d] + __ldg(p.deg + (size_t)k * p.nvars + d) * p.nq[d] : 0);
-        run_products<CPLX>(T, eo + pt, BM, p.qdig, p.DP, 0, p.L, 1, p.Qtot, p.dsplit, p.nvars, p.nq[p.nvars - 1], valid, S + pt, SP, p.L);
+        run_products<CPLX>(T, eo + pt, BM, p.qdig, p.DP, 0, p.L, 1, p.Qtot, p.dsplit, p.nvars, p.nq[p.nvars - 1], valid, S + pt, SP, LP);
+        for (int t = p.L; t < LP; t++) { S[t * SP + pt] = 0.0; if (CPLX) S[(LP + t) * SP + pt] = 0.0; }
       }
       mbar_arrive(s_full);
-      // ---- per stage: f tile by TMA, prefix values P, point -> (tail index, prefix slot) map ----
-      // prefix block of the stage's first point = hi*nql + lo (lo = digit of the last prefix variable); the product over
-      // the other prefix variables is cached per hi — it changes once every nql*L points
+      // ---- per stage: f rows of the chunk by TMA, the prefix value P of the chunk's block, the chunk descriptor ----
+      // block = hi*nql + lo (lo = digit of the last prefix variable); the product over the other prefix variables is
+      // cached per hi — it changes once every nql*L points
       const int nql = p.dsplit > 0 ? p.nq[p.dsplit - 1] : 1;
       const int eo_last = p.dsplit > 0 ? (int)eo[(p.dsplit - 1) * BM + (pt < BM ? pt : 0)] : 0;
-      const long long blk0 = (p.q0 + (long long)c0 * VKQ) / p.L;
-      int rem = (int)((p.q0 + (long long)c0 * VKQ) - blk0 * p.L);
-      long long hi = blk0 / nql;
-      int lo = (int)(blk0 - hi * nql);
+      long long blk = cm.b0 + c0 / cm.cpb;
+      int j = c0 % cm.cpb;
+      long long hi = blk / nql;
+      int lo = (int)(blk - hi * nql);
       long long c_hi = -1;
       double cbr = 1.0, cbi = 0.0;
       for (int c = c0; c < c1; c++) {
         mbar_wait(&empty[s], ph ^ 1u);
         unsigned char *st = ring + (size_t)s * p.stage_bytes;
+        int tlo, thi;
+        cm.range(blk, j, tlo, thi);
         if (pt == 0) {
+          const long long row = thi > tlo ? blk * cm.L + tlo - p.q0 : 0;     // first f row of the chunk (relative to q0)
           mbar_arrive_expect_tx(&full[s], TL::B_BYTES);
-          tma_load_2d(st, &tmapB, &full[s], tn * BN, c * VKQ);
+          tma_load_2d(st, &tmapB, &full[s], tn * BN, (int)row);
+          *reinterpret_cast<int2 *>(st + D_OFF) = make_int2(tlo * SP, (thi - tlo + 3) >> 2);   // S row offset, k-steps
         }
-        double *Pst = reinterpret_cast<double *>(st + P_OFF);
         if (pt < BM) {
-          for (int pb = 0; pb < p.npfx; pb++) {
-            int l = lo + pb;
-            long long h = hi;
-            while (l >= nql) { l -= nql; h++; }
-            const long long qb = (h * nql + l) * p.L;                       // first point of the block
-            double vr = 0.0, vi = 0.0;
-            if (valid && qb < p.Qtot) {
-              if (p.dsplit > 0) {
-                if (h != c_hi) {
-                  const long long qh = h * nql * p.L;
-                  cbr = 1.0; cbi = 0.0;
-                  table_product<CPLX>(T, eo + pt, BM, p.qdig + (size_t)qh * p.DP, 0, p.dsplit - 1, cbr, cbi);
-                  c_hi = h;
-                  const long long qn = qh + (long long)nql * p.L;           // digit row of the next run: into L1 ahead of use
-                  if (qn < p.Qtot) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p.qdig + (size_t)qn * p.DP));
-                }
-                table_mul<CPLX>(T, eo_last + l, cbr, cbi, vr, vi);
-              } else vr = 1.0;
-            }
-            Pst[pb * SP + pt] = vr;
-            if (CPLX) Pst[(p.npfx + pb) * SP + pt] = vi;
+          const long long qb = blk * cm.L;                                   // first point of the block
+          double vr = 0.0, vi = 0.0;
+          if (valid && qb < p.Qtot) {
+            if (p.dsplit > 0) {
+              if (hi != c_hi) {
+                const long long qh = hi * nql * cm.L;
+                cbr = 1.0; cbi = 0.0;
+                table_product<CPLX>(T, eo + pt, BM, p.qdig + (size_t)qh * p.DP, 0, p.dsplit - 1, cbr, cbi);
+                c_hi = hi;
+                const long long qn = qh + (long long)nql * cm.L;             // digit row of the next run: into L1 ahead of use
+                if (qn < p.Qtot) asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p.qdig + (size_t)qn * p.DP));
+              }
+              table_mul<CPLX>(T, eo_last + lo, cbr, cbi, vr, vi);
+            } else vr = 1.0;
           }
-        }
-        if (pt < VKQ) {
-          const int t = rem + pt;                                          // offset from the first point of block blk
-          const int pb = t / p.L;
-          reinterpret_cast<int2 *>(st + IDX_OFF)[pt] = make_int2((t - pb * p.L) * SP, pb * SP);
+          double *Pst = reinterpret_cast<double *>(st + P_OFF);
+          Pst[pt] = vr;
+          if (CPLX) Pst[SP + pt] = vi;
         }
         mbar_arrive(&full[s]);
-        rem += VKQ;
-        while (rem >= p.L) { rem -= p.L; if (++lo == nql) { lo = 0; hi++; } }
+        if (++j == cm.cpb) { j = 0; blk++; if (++lo == nql) { lo = 0; hi++; } }
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
@@ -232,61 +259,85 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
 #pragma unroll
         for (int b = 0; b < WN; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
       mbar_wait(s_full, (unsigned)sidx & 1u);
-      const double *Sr = S + rbase;
-      const double *Si = S + (size_t)p.L * SP + rbase;
 
       for (int c = c0; c < c1; c++, it++) {
         const bool mine = KG == 1 || (it % KG) == kg;
         if (mine) {
           mbar_wait(&full[s], ph);
           const unsigned char *st = ring + (size_t)s * p.stage_bytes;
-          const double *bs = reinterpret_cast<const double *>(st) + g;
-          const double *bs2 = reinterpret_cast<const double *>(st) + 2 * g;
-          const double *Pr = reinterpret_cast<const double *>(st + P_OFF) + rbase;
-          const double *Pi = Pr + (size_t)p.npfx * SP;
-          const int2 *idx = reinterpret_cast<const int2 *>(st + IDX_OFF);
-          double last = 0.0;
+          const int2 desc = *reinterpret_cast<const int2 *>(st + D_OFF);
+          const double *bs = reinterpret_cast<const double *>(st) + kl * LDB + g;
+          const double *bs2 = reinterpret_cast<const double *>(st) + kl * LDB + 2 * g;
+          const double *Sr = S + desc.x + kl * SP + rbase;                    // S rows tlo + k of my rows
+          const double *Si = Sr + (size_t)LP * SP;
+          // G = sum over the chunk's points of S (x) f — the block's prefix value P is applied once, below
+          double G[WM][WN][2];
 #pragma unroll
-          for (int ks = 0; ks < VKQ / 4; ks++) {
-            const int k = ks * 4 + kl;
-            const int2 ix = idx[k];
+          for (int a = 0; a < WM; a++)
+#pragma unroll
+            for (int b = 0; b < WN; b++) G[a][b][0] = G[a][b][1] = 0.0;
+          int depi = 0;
+          auto kstep = [&](int ks) {
             double are[WM], aim[WM];
 #pragma unroll
             for (int a = 0; a < WM; a++) {
-              const double sr = Sr[ix.x + a * 8], pr = Pr[ix.y + a * 8];
-              if (!CPLX) are[a] = sr * pr;
-              else {
-                const double si = Si[ix.x + a * 8], pi = Pi[ix.y + a * 8];
-                are[a] = sr * pr - si * pi;
-                aim[a] = sr * pi + si * pr;
-              }
+              are[a] = Sr[ks * 4 * SP + a * 8];
+              if (CPLX) aim[a] = Si[ks * 4 * SP + a * 8];
             }
             double bfr[WN], bsw[WN];
             if (PAIRED) {
 #pragma unroll
               for (int b2 = 0; b2 < WN / 2; b2++) {
-                const double2 v = *reinterpret_cast<const double2 *>(bs2 + k * LDB + 16 * b2);
+                const double2 v = *reinterpret_cast<const double2 *>(bs2 + ks * 4 * LDB + 16 * b2);
                 bfr[2 * b2] = v.x; bfr[2 * b2 + 1] = v.y;
                 if (CPLX) { bsw[2 * b2] = flip_sign(v.y, 0x80000000u); bsw[2 * b2 + 1] = v.x; }
               }
             } else {
 #pragma unroll
               for (int b = 0; b < WN; b++) {
-                bfr[b] = bs[k * LDB + b * 8];
-                if (CPLX) bsw[b] = flip_sign(bs[k * LDB + b * 8 + ((g & 1) ? -1 : 1)], sgn);
+                bfr[b] = bs[ks * 4 * LDB + b * 8];
+                if (CPLX) bsw[b] = flip_sign(bs[ks * 4 * LDB + b * 8 + ((g & 1) ? -1 : 1)], sgn);
               }
             }
 #pragma unroll
             for (int a = 0; a < WM; a++)
 #pragma unroll
               for (int b = 0; b < WN; b++) {
-                dmma884(acc[a][b][0], acc[a][b][1], are[a], bfr[b]);
-                if (CPLX) dmma884(acc[a][b][0], acc[a][b][1], aim[a], bsw[b]);
+                dmma884(G[a][b][0], G[a][b][1], are[a], bfr[b]);
+                if (CPLX) dmma884(G[a][b][0], G[a][b][1], aim[a], bsw[b]);
               }
-            if (ks == VKQ / 4 - 1) last = are[WM - 1] + bfr[WN - 1];
+            depi = __double2loint(bfr[WN - 1]) ^ __double2loint(are[WM - 1]);
+          };
+          if (desc.y == VKQ / 4) {
+#pragma unroll
+            for (int ks = 0; ks < VKQ / 4; ks++) kstep(ks);
+          } else {
+#pragma unroll 2
+            for (int ks = 0; ks < desc.y; ks++) kstep(ks);
           }
-          // release the stage: the arrive's address depends on the last fragment registers of the stage
-          const unsigned dep = (unsigned)__double2hiint(last) & p.zero;
+          // acc += P (x) G : one prefix value per basis row of the lane
+          const double *Pst = reinterpret_cast<const double *>(st + P_OFF) + rbase;
+#pragma unroll
+          for (int a = 0; a < WM; a++) {
+            const double pr = Pst[a * 8];
+            if (!CPLX) {
+#pragma unroll
+              for (int b = 0; b < WN; b++) { acc[a][b][0] = fma(pr, G[a][b][0], acc[a][b][0]); acc[a][b][1] = fma(pr, G[a][b][1], acc[a][b][1]); }
+            } else {
+              const double pi = Pst[SP + a * 8];
+#pragma unroll
+              for (int idx = 0; idx < WN; idx++) {
+                // (re, im) of one complex column = the two values acc_pair hands out together
+                double *gr, *gi, *ar, *ai;
+                if (PAIRED) { const int b2 = idx >> 1, e = idx & 1; gr = &G[a][2 * b2][e]; gi = &G[a][2 * b2 + 1][e]; ar = &acc[a][2 * b2][e]; ai = &acc[a][2 * b2 + 1][e]; }
+                else { gr = &G[a][idx][0]; gi = &G[a][idx][1]; ar = &acc[a][idx][0]; ai = &acc[a][idx][1]; }
+                *ar += pr * *gr - pi * *gi;
+                *ai += pr * *gi + pi * *gr;
+              }
+            }
+          }
+          // release the stage: the arrive's address depends on the last fragment registers read from it
+          const unsigned dep = ((unsigned)depi ^ (unsigned)__double2loint(Pst[0])) & p.zero;
           __syncwarp();
           if (lane == 0) mbar_arrive(&empty[s], dep);
         }
@@ -427,7 +478,7 @@ const VVariant V_CPLX[] = {{1, 128, 16, "128x16"}, {2, 128, 32, "128x32"}, {3, 1
 struct VPlan {
   int vi;                        // index into V_REAL / V_CPLX
   int tiles_r, tiles_n, nchunk, grid, rem_tiles;
-  int dsplit, L, npfx, stages, stage_bytes;
+  int dsplit, L, LP, stages, stage_bytes;
   size_t smem, ws_bytes;
 };
 
@@ -437,24 +488,61 @@ int sm_count_v(int device) {
   return n;
 }
 
-template <class TL> void size_ring(const pspace_ctx *c, VPlan &pl) {
-  // tail = as many trailing variables as keep S within its budget; the ring gets what is left of the 227 KB
-  const size_t budget = 72 * 1024;
-  int ds = c->nvars;
-  long long L = 1;
-  while (ds > 0) {
-    const long long Ln = L * c->nq[ds - 1];
-    if (TL::s_bytes((int)std::min<long long>(Ln, 1 << 20)) > budget || Ln > (1 << 20)) break;
-    L = Ln; ds--;
+// tile variant (fewest column tiles first — every column tile regenerates the operand —, then the least padded work) and
+// the workspace bound, both independent of the tail length
+int plan_v(const pspace_ctx *c, const pspace_project_args *a, VPlan &pl) {
+  const int ncols_d = a->ncols * c->width, nk = a->k1 - a->k0;
+  const VVariant *vs = c->is_complex ? V_CPLX : V_REAL;
+  const int nv = c->is_complex ? 6 : 8, nv_all = c->is_complex ? 6 : 11;
+  int best = -1;
+  if (a->variant > 0) {
+    for (int i = 0; i < nv_all; i++) if (vs[i].id == a->variant) best = i;
+    if (best < 0) return ps_fail(PSPACE_EINVAL, "unknown vector tile variant %d", a->variant);
+  } else {
+    long long best_tn = 0, best_cost = 0;
+    for (int i = 0; i < nv; i++) {
+      const long long tn = (ncols_d + vs[i].BN - 1) / vs[i].BN, trr = (nk + vs[i].BM - 1) / vs[i].BM;
+      const long long cost = tn * vs[i].BN * trr * vs[i].BM;
+      if (best < 0 || tn < best_tn || (tn == best_tn && cost < best_cost)) { best = i; best_tn = tn; best_cost = cost; }
+    }
   }
-  if (ds == c->nvars) { ds = c->nvars - 1; L = c->nq[ds]; }      // a single rule (<= 20 points) always fits
-  pl.dsplit = ds; pl.L = (int)L;
-  pl.npfx = (int)((VKQ + L - 2) / L) + 1;
-  pl.stage_bytes = TL::stage_bytes(pl.npfx);
-  const size_t head = TL::header_bytes(pl.L, c->nvars, c->tsz);
-  const size_t avail = (size_t)227 * 1024 - head - 1024 - 256;
-  pl.stages = (int)std::max<size_t>(2, std::min<size_t>(8, avail / pl.stage_bytes));
+  pl.vi = best;
+  pl.tiles_n = (ncols_d + vs[best].BN - 1) / vs[best].BN;
+  pl.tiles_r = (nk + vs[best].BM - 1) / vs[best].BM;
+  // stream-K partial tiles: 2 per persistent CTA (an upper bound that does not depend on the chunking)
+  pl.ws_bytes = (size_t)sm_count_v(c->device) * 2 * vs[best].BM * vs[best].BN * sizeof(double);
+  return PSPACE_OK;
+}
+
+// Tail length L = a product of trailing rule sizes: the candidate with the longest average chunk (chunks are cut at
+// multiples of 64 inside a prefix block, so avg = L / ceil(L/64)) whose tail table leaves room for 3 pipeline stages.
+template <class TL> int size_ring(const pspace_ctx *c, const pspace_project_args *a, VPlan &pl) {
+  const size_t cap = (size_t)227 * 1024 - 1024 - 256;
+  int best_ds = -1;
+  long long best_L = 1, L = 1;
+  double best_avg = -1.0;
+  for (int ds = c->nvars - 1; ds >= 0; ds--) {
+    L *= c->nq[ds];
+    if (L > 8192) break;
+    const int LP = (int)L + 4, cpb = (int)((L + VKQ - 1) / VKQ);   // a clipped chunk may start off a multiple of 4: its last k-step reads up to row L + 2
+    const size_t need = TL::header_bytes(LP, c->nvars, c->tsz) + 3 * (size_t)TL::stage_bytes() + 256;
+    if (need > cap) break;
+    const double avg = (double)L / cpb;
+    if (avg > best_avg + 1e-9) { best_avg = avg; best_ds = ds; best_L = L; }
+  }
+  if (best_ds < 0) return ps_fail(PSPACE_EINVAL, "vector projection: the tail table of one rule does not fit shared memory");
+  pl.dsplit = best_ds; pl.L = (int)best_L; pl.LP = (int)best_L + 4;
+  pl.stage_bytes = TL::stage_bytes();
+  const size_t head = TL::header_bytes(pl.LP, c->nvars, c->tsz);
+  pl.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (cap - head - 256) / pl.stage_bytes));
   pl.smem = head + (size_t)pl.stages * pl.stage_bytes + (2 * pl.stages + 2) * 8 + 1024;
+  const long long nch = ChunkMap(a->q0, a->q1, pl.L).nchunk();
+  if (nch > 0x7fffffffLL) return ps_fail(PSPACE_EINVAL, "vector projection: %lld chunks", nch);
+  pl.nchunk = (int)nch;
+  const long long ntiles = (long long)pl.tiles_r * pl.tiles_n;
+  pl.grid = (int)std::max<long long>(1, std::min<long long>(sm_count_v(c->device), ntiles * pl.nchunk));
+  pl.rem_tiles = (int)(ntiles % pl.grid);
+  return PSPACE_OK;
 }
 
 template <class TL> int launch_v(const pspace_ctx *c, VParams &p, const VPlan &pl, const double *d_in, cudaStream_t st) {
@@ -478,34 +566,6 @@ template <class TL> int launch_v(const pspace_ctx *c, VParams &p, const VPlan &p
     k_vfixup<<<dim3(pl.rem_tiles, (TL::BM * TL::BN + VFX_ELEMS - 1) / VFX_ELEMS), 256, 0, st>>>(p, pl.grid, TL::BM, TL::BN);
     PS_LAUNCH_CHECK(c);
   }
-  return PSPACE_OK;
-}
-
-int plan_v(const pspace_ctx *c, const pspace_project_args *a, VPlan &pl) {
-  const int ncols_d = a->ncols * c->width, nk = a->k1 - a->k0;
-  const VVariant *vs = c->is_complex ? V_CPLX : V_REAL;
-  const int nv = c->is_complex ? 6 : 8, nv_all = c->is_complex ? 6 : 11;
-  int best = -1;
-  if (a->variant > 0) {
-    for (int i = 0; i < nv_all; i++) if (vs[i].id == a->variant) best = i;
-    if (best < 0) return ps_fail(PSPACE_EINVAL, "unknown vector tile variant %d", a->variant);
-  } else {
-    // fewest column tiles first (every column tile regenerates the operand), then the least padded work
-    long long best_tn = 0, best_cost = 0;
-    for (int i = 0; i < nv; i++) {
-      const long long tn = (ncols_d + vs[i].BN - 1) / vs[i].BN, trr = (nk + vs[i].BM - 1) / vs[i].BM;
-      const long long cost = tn * vs[i].BN * trr * vs[i].BM;
-      if (best < 0 || tn < best_tn || (tn == best_tn && cost < best_cost)) { best = i; best_tn = tn; best_cost = cost; }
-    }
-  }
-  pl.vi = best;
-  pl.tiles_n = (ncols_d + vs[best].BN - 1) / vs[best].BN;
-  pl.tiles_r = (nk + vs[best].BM - 1) / vs[best].BM;
-  pl.nchunk = (int)((a->q1 - a->q0 + VKQ - 1) / VKQ);
-  const long long ntiles = (long long)pl.tiles_r * pl.tiles_n;
-  pl.grid = (int)std::max<long long>(1, std::min<long long>(sm_count_v(c->device), ntiles * pl.nchunk));
-  pl.rem_tiles = (int)(ntiles % pl.grid);
-  pl.ws_bytes = pl.rem_tiles > 0 ? (size_t)pl.grid * 2 * vs[best].BM * vs[best].BN * sizeof(double) : 0;
   return PSPACE_OK;
 }
 }  // namespace
@@ -537,14 +597,15 @@ int ps_vproject(const pspace_ctx *c, const pspace_project_args *a, const double 
   p.q0 = a->q0; p.q1 = a->q1; p.Qtot = c->Q;
   p.k0 = a->k0; p.nk = a->k1 - a->k0; p.ncols_d = a->ncols * c->width; p.nvars = c->nvars; p.DP = c->DP; p.tsz = c->tsz;
   for (int d = 0; d < PSPACE_MAX_VARS; d++) { p.toff[d] = d < c->nvars ? c->toff[d] : 0; p.nq[d] = d < c->nvars ? c->nq[d] : 1; }
-  p.tiles_r = pl.tiles_r; p.tiles_n = pl.tiles_n; p.nchunk = pl.nchunk;
+  p.tiles_r = pl.tiles_r; p.tiles_n = pl.tiles_n;
   p.accumulate = a->accumulate; p.zero = 0;
   const VVariant &v = (c->is_complex ? V_CPLX : V_REAL)[pl.vi];
   const int key = (c->is_complex ? 100 : 0) + v.id;
 #define PS_VCASE(K, TL)                                                                              \
   case K:                                                                                            \
-    size_ring<TL>(c, pl);                                                                            \
-    p.dsplit = pl.dsplit; p.L = pl.L; p.npfx = pl.npfx; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; \
+    if ((rc = size_ring<TL>(c, a, pl))) break;                                                       \
+    p.dsplit = pl.dsplit; p.L = pl.L; p.LP = pl.LP; p.stages = pl.stages; p.stage_bytes = pl.stage_bytes; \
+    p.nchunk = pl.nchunk;                                                                            \
     rc = launch_v<TL>(c, p, pl, d_in, st);                                                           \
     break;
   switch (key) {
@@ -558,7 +619,7 @@ int ps_vproject(const pspace_ctx *c, const pspace_project_args *a, const double 
 #undef PS_VCASE
   if (rc) return rc;
   pspace_ctx *mc = const_cast<pspace_ctx *>(c);
-  mc->plan_kernel = "factored operand (P x S in shared memory), tma + mbarrier warp-specialised, persistent stream-K";
+  mc->plan_kernel = "factored operand (tail table in shared memory, prefix applied per block), tma + mbarrier warp-specialised, persistent stream-K";
   mc->plan_chunk_pts = VKQ;
   mc->plan_flop = 2.0 * (double)p.nk * (double)p.ncols_d * (double)(a->q1 - a->q0) * (c->is_complex ? 2.0 : 1.0);
   char buf[320];
