@@ -129,6 +129,21 @@ struct ChunkMap {
   }
 };
 
+// S[t][row] (and the zero pad rows [L, LP)) of one row tile: thread -> (row, part), part p of nthreads/BM covers the tail
+// points [p*per, (p+1)*per).
+template <bool CPLX>
+__device__ __forceinline__ void fill_tail_rows(const VParams &p, const double *T, const unsigned short *eo, double *S, int LP, int SP,
+                                            int BM, int nthreads, int tid, int tr) {
+  const int nparts = nthreads / BM, row = tid % BM, part = tid / BM;
+  if (part >= nparts) return;
+  const int per = (p.L + nparts - 1) / nparts, t0 = part * per, n = min(p.L, t0 + per) - t0;
+  const bool valid = tr * BM + row < p.nk;
+  if (n > 0)
+    psf::run_products<CPLX>(T, eo + row, BM, p.qdig, p.DP, t0, n, 1, p.Qtot, p.dsplit, p.nvars, p.nq[p.nvars - 1], valid, S + t0 * SP + row, SP, LP);
+  if (part == nparts - 1)
+    for (int t = p.L; t < LP; t++) { S[t * SP + row] = 0.0; if (CPLX) S[(LP + t) * SP + row] = 0.0; }
+}
+
 template <class TL>
 __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant__ VParams p, const __grid_constant__ CUtensorMap tmapB) {
   constexpr int WM = TL::WM, WN = TL::WN, RG = TL::RG, KG = TL::KG, W = TL::W, BM = TL::BM, BN = TL::BN;
@@ -136,6 +151,9 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
   constexpr bool CPLX = TL::CPLX;
   constexpr bool PAIRED = CPLX && (WN % 2) == 0;
   constexpr int VNCW = TL::NCW, VT = TL::NT;
+  // the consumers help to write the tail table in the real build; the complex kernels have no registers to spare for it
+  // (measured: -20 % on cfg4 when the fill code shares the consumer's register allocation)
+  constexpr bool ALLFILL = !CPLX;
 
   extern __shared__ __align__(1024) unsigned char smem[];
   const int LP = p.LP;                                                                     // S rows incl. the zero pad
@@ -147,7 +165,7 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
   const int STAGES = p.stages;
   unsigned long long *full = reinterpret_cast<unsigned long long *>(ring + (size_t)STAGES * p.stage_bytes);
   unsigned long long *empty = full + STAGES;
-  unsigned long long *s_full = empty + STAGES, *s_free = s_full + 1;
+  unsigned long long *s_full = empty + STAGES, *s_free = s_full + 1, *eo_full = s_full + 2;
   constexpr int P_OFF = TL::B_BYTES, D_OFF = TL::B_BYTES + W * SP * 8;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -161,12 +179,15 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
   const double *T = tab_smem ? Ts : p.Tw;
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1 + VNPT); mbar_init(&empty[s], RG); }
-    mbar_init(s_full, VNPT);
+    mbar_init(s_full, ALLFILL ? VT : VNPT);
     mbar_init(s_free, VNCW);
+    mbar_init(eo_full, VNPT);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
 
+  // The tail table S of a segment's row tile is written by ALL warps (the consumers have nothing else to do until it
+  // exists): fill_tail_rows, called before the accumulators of the segment come to life.
   if (warp >= VNCW) {
     // =========================== PRODUCERS: TMA + the factor tables =====================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(56));
@@ -182,11 +203,15 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
       const bool valid = pt < BM && k < p.k0 + p.nk;
       // ---- per segment: row offsets and the tail table S of this row tile (rows [L, LP) are the zero pad) ----
       if (sidx > 0) mbar_wait(s_free, (unsigned)(sidx - 1) & 1u);
-      if (pt < BM) {
+      if (pt < BM)
         for (int d = 0; d < p.nvars; d++)
           eo[d * BM + pt] = (unsigned short)(valid ? p.toff[d] + __ldg(p.deg + (size_t)k * p.nvars + d) * p.nq[d] : 0);
-        run_products<CPLX>(T, eo + pt, BM, p.qdig, p.DP, 0, p.L, 1, p.Qtot, p.dsplit, p.nvars, p.nq[p.nvars - 1], valid, S + pt, SP, LP);
-        for (int t = p.L; t < LP; t++) { S[t * SP + pt] = 0.0; if (CPLX) S[(LP + t) * SP + pt] = 0.0; }
+      if (ALLFILL) {
+        mbar_arrive(eo_full);                        // the row offsets of the tile are in place: everyone fills S
+        mbar_wait(eo_full, (unsigned)sidx & 1u);
+        fill_tail_rows<CPLX>(p, T, eo, S, LP, SP, BM, VT, tid, tr);
+      } else {
+        fill_tail_rows<CPLX>(p, T, eo, S, LP, SP, BM, VNPT, pt, tr);
       }
       mbar_arrive(s_full);
       // ---- per stage: f rows of the chunk by TMA, the prefix value P of the chunk's block, the chunk descriptor ----
@@ -253,12 +278,19 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
       int tile, c0, c1, slot;
       wk.segment(gcta, sidx, tile, c0, c1, slot);
       const int tn = tile % p.tiles_n, tr = tile / p.tiles_n;
+      // every consumer warp has left the previous segment (s_free) and the row offsets exist (eo_full): write my share of S
+      if (ALLFILL) {
+        if (sidx > 0) mbar_wait(s_free, (unsigned)(sidx - 1) & 1u);
+        mbar_wait(eo_full, (unsigned)sidx & 1u);
+        fill_tail_rows<CPLX>(p, T, eo, S, LP, SP, BM, VT, tid, tr);
+        mbar_arrive(s_full);
+      }
+      mbar_wait(s_full, (unsigned)sidx & 1u);
       double acc[WM][WN][2];
 #pragma unroll
       for (int a = 0; a < WM; a++)
 #pragma unroll
         for (int b = 0; b < WN; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-      mbar_wait(s_full, (unsigned)sidx & 1u);
 
       for (int c = c0; c < c1; c++, it++) {
         const bool mine = KG == 1 || (it % KG) == kg;
@@ -524,18 +556,23 @@ template <class TL> int size_ring(const pspace_ctx *c, const pspace_project_args
   for (int ds = c->nvars - 1; ds >= 0; ds--) {
     L *= c->nq[ds];
     if (L > 8192) break;
-    const int LP = (int)L + 4, cpb = (int)((L + VKQ - 1) / VKQ);   // a clipped chunk may start off a multiple of 4: its last k-step reads up to row L + 2
+    // zero pad rows after the table: the last k-step of a block's last chunk reads up to 3 rows past L - 1 unless both L
+    // and the range's offset into its first block are multiples of 4 (then only a clipped END is ragged, and there the
+    // extra rows of f lie past the range and come back as zeros from TMA)
+    const int pad = ((L % 4) != 0 || ((a->q0 % L) % 4) != 0) ? 4 : 0;
+    const int LP = (int)L + pad, cpb = (int)((L + VKQ - 1) / VKQ);
     const size_t need = TL::header_bytes(LP, c->nvars, c->tsz) + 3 * (size_t)TL::stage_bytes() + 256;
     if (need > cap) break;
     const double avg = (double)L / cpb;
     if (avg > best_avg + 1e-9) { best_avg = avg; best_ds = ds; best_L = L; }
   }
   if (best_ds < 0) return ps_fail(PSPACE_EINVAL, "vector projection: the tail table of one rule does not fit shared memory");
-  pl.dsplit = best_ds; pl.L = (int)best_L; pl.LP = (int)best_L + 4;
+  pl.dsplit = best_ds; pl.L = (int)best_L;
+  pl.LP = (int)best_L + (((best_L % 4) != 0 || ((a->q0 % best_L) % 4) != 0) ? 4 : 0);
   pl.stage_bytes = TL::stage_bytes();
   const size_t head = TL::header_bytes(pl.LP, c->nvars, c->tsz);
   pl.stages = (int)std::max<size_t>(2, std::min<size_t>(8, (cap - head - 256) / pl.stage_bytes));
-  pl.smem = head + (size_t)pl.stages * pl.stage_bytes + (2 * pl.stages + 2) * 8 + 1024;
+  pl.smem = head + (size_t)pl.stages * pl.stage_bytes + (2 * pl.stages + 3) * 8 + 1024;
   const long long nch = ChunkMap(a->q0, a->q1, pl.L).nchunk();
   if (nch > 0x7fffffffLL) return ps_fail(PSPACE_EINVAL, "vector projection: %lld chunks", nch);
   pl.nchunk = (int)nch;
