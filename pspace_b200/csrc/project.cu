@@ -789,8 +789,13 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
         if (MASKED && mirroff >= 0) {
           double *md = p.out + mirroff + col;
           double w0 = a0, w1 = a1;
-          if (col < p.ncols_d) md[0] = p.accumulate ? md[0] + w0 : w0;
-          if (col + 1 < p.ncols_d) md[1] = p.accumulate ? md[1] + w1 : w1;
+          if (col + 1 < p.ncols_d && ((reinterpret_cast<size_t>(md) & 15) == 0)) {
+            if (p.accumulate) { const double2 o = *reinterpret_cast<double2 *>(md); w0 += o.x; w1 += o.y; }
+            *reinterpret_cast<double2 *>(md) = make_double2(w0, w1);
+          } else {
+            if (col < p.ncols_d) md[0] = p.accumulate ? md[0] + w0 : w0;
+            if (col + 1 < p.ncols_d) md[1] = p.accumulate ? md[1] + w1 : w1;
+          }
         }
       }
     }
@@ -873,6 +878,7 @@ __global__ void __launch_bounds__(256) k_fixup(const __grid_constant__ ProjParam
   __syncthreads();
   const int npieces = s_n;
   // blockIdx.y splits the tile's elements, so that a few big remainder tiles still fill the machine
+  bool pushed = false;
   for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < BM * BN; e += gridDim.y * blockDim.x) {
     const int r = e / BN, cc = e % BN;
     double sum = 0.0;
@@ -882,7 +888,7 @@ __global__ void __launch_bounds__(256) k_fixup(const __grid_constant__ ProjParam
       const int pt = tile / p.tiles_n;
       const int owner = min(p.peer_world - 1, pt / p.peer_lp), lp = pt - owner * p.peer_lp;
       p.peer_recv[owner][((size_t)(p.peer_rank * p.peer_lp + lp) * BM + r) * p.peer_ncols_pad + (size_t)tn * BN + cc] = sum;
-      __threadfence_system();
+      pushed = true;
       continue;
     }
     const int col = col0 + cc;
@@ -907,6 +913,7 @@ __global__ void __launch_bounds__(256) k_fixup(const __grid_constant__ ProjParam
     *dst = p.accumulate ? *dst + sum : sum;
     if (mirroff >= 0) { double *md = p.out + mirroff + col; *md = p.accumulate ? *md + sum : sum; }
   }
+  if (pushed) __threadfence_system();      // peer stores of this thread must have landed at their owners before the kernel completes
 }
 
 // Second half of the fused collective.  Every rank owns peer_lp consecutive pair tiles; after all ranks' pushes have

@@ -307,6 +307,9 @@ def test_factored_operand_kernels_vs_oracle_and_panel_kernels(cplx):
         ([("normal", 0.5 + pert, 1.5, 19)], 0, None),                                                       # one rule of 20 points
         ([("normal", 0.0, 1.0, 1), ("uniform", 0.0, 1.0, 1), ("exponential", 0.0, 1.0, 1)] * 3, 1, None),     # 9 variables, nq = 2
         ([("uniform", -1.0, 1.0, 2), ("normal", 0.2, 0.7 + pert, 2), ("exponential", 0.0, 1.0, 2)], 0, [7, 3, 5]),  # nq != dmax+1
+        ([("normal", 0.1 * d + pert * (d == 0), 1.0 + 0.1 * d, 3) for d in range(4)] + [("uniform", -1.0, 1.0, 3), ("exponential", 0.0, 1.0, 3)],
+         1, None),                                                                    # 6 variables, nq = 4: L = 64, N = 84, Q = 4096
+        ([("uniform", 0.0, 1.0, 7), ("normal", 0.0, 1.0 + pert, 7), ("exponential", 0.0, 1.0, 3)], 0, None),   # tensor: N = Q = 256, rules of 8, 8, 4 points
     ]
     nvar_v = 6 if cplx else 8
     for ps, bt, nq in containers:
