@@ -174,6 +174,23 @@ def bind(complex_=False):
             L.pspace_host_evaluate_expansion(self.ptr, VV.shape[1], VV.ctypes.data, U.ctypes.data)
             return U
 
+        def adjointStates(self, v, adj, nnodes, ndvpn):
+            """(u_q, psi_q) at every quadrature point from TACS-interleaved stochastic vectors: (Q, 2m), m = nnodes*ndvpn."""
+            m = nnodes * ndvpn
+            vv, aa = np.ascontiguousarray(v, dtype=dtype).ravel(), np.ascontiguousarray(adj, dtype=dtype).ravel()
+            assert vv.size == aa.size == self.getNumBasisTerms() * m
+            UP = np.zeros((self.getNumQuadraturePoints(), 2 * m), dtype=dtype)
+            L.pspace_host_adjoint_states(self.ptr, nnodes, ndvpn, vv.ctypes.data, aa.ctypes.data, UP.ctypes.data)
+            return UP
+
+        def adjointProduct(self, G, scale=1.0, dfdx=None):
+            """dfdx[n] += scale * sum_q w_q basis(0, z_q) G[q, n]  (addAdjResProduct, TACSStochasticElement.cpp:548-637)."""
+            GG = np.ascontiguousarray(G, dtype=dtype).reshape(self.getNumQuadraturePoints(), -1)
+            out = np.zeros(GG.shape[1], dtype=dtype) if dfdx is None else dfdx
+            sc = np.array([scale], dtype=dtype)
+            L.pspace_host_adjoint_product(self.ptr, GG.shape[1], sc.ctypes.data, GG.ctypes.data, out.ctypes.data)
+            return out
+
         def projectVector(self, f):
             ff = np.ascontiguousarray(f, dtype=dtype).reshape(self.getNumQuadraturePoints(), -1)
             F = np.zeros((self.getNumBasisTerms(), ff.shape[1]), dtype=dtype)

@@ -58,6 +58,12 @@ class ParameterContainer {
   void projectMatrix(int m2, const scalar *J, scalar *C);
   // pair window [i0,i1) x [j0,j1):  C[((i-i0)*(j1-j0) + (j-j0))*m2 + c]
   void projectMatrixWindow(int m2, const scalar *J, int i0, int i1, int j0, int j1, scalar *C);
+  // adjoint-residual product (TACSStochasticElement::addAdjResProduct, examples/stacs/cpp/TACSStochasticElement.cpp:548-637)
+  // around the caller's deterministic element; m = nnodes*ndvpn; v, adj = TACS-interleaved stochastic vectors [nnodes*N*ndvpn]:
+  //   adjointStates : UP[q*2m + c] = u_q[c] (c < m), UP[q*2m + m + c] = psi_q[c]     (getDeterministicStates / -Adjoint, :53-120)
+  //   adjointProduct: dfdx[n] += scale * sum_q w_q basis(0,z_q) G[q*dvLen + n]      (G = the element's integrand per point)
+  void adjointStates(int nnodes, int ndvpn, const scalar *v, const scalar *adj, scalar *UP);
+  void adjointProduct(int dvLen, scalar scale, const scalar *G, scalar *dfdx);
   // device-pointer forms for callers that keep J / C resident (q-range [q0,q1) = this rank's shard; d_J holds
   // rows q0..q1-1).  `stream` is a cudaStream_t.  Returns the C-ABI status (0 = ok).
   int projectVectorDevice(int m, const scalar *d_f, scalar *d_F, long long q0, long long q1, void *stream);

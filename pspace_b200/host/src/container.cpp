@@ -195,6 +195,35 @@ void ParameterContainer::evaluateExpansion(int m, const scalar *V, scalar *U) {
   pspace_cuda_free(du);
 }
 
+void ParameterContainer::adjointStates(int nnodes, int ndvpn, const scalar *v, const scalar *adj, scalar *UP) {
+  ensureContext();
+  const size_t w = PSPACE_SCALAR_WIDTH, m = (size_t)nnodes * ndvpn;
+  const size_t vb = sizeof(double) * w * (size_t)tnum_basis_terms * m, ub = sizeof(double) * w * (size_t)tnum_quadrature_points * 2 * m;
+  void *dv = 0, *da = 0, *du = 0;
+  PS_MUST(pspace_cuda_malloc(&dv, vb));
+  PS_MUST(pspace_cuda_malloc(&da, vb));
+  PS_MUST(pspace_cuda_malloc(&du, ub));
+  PS_MUST(pspace_cuda_memcpy(dv, v, vb, 1));
+  PS_MUST(pspace_cuda_memcpy(da, adj, vb, 1));
+  PS_MUST(pspace_cuda_adjoint_states(ctx, nnodes, ndvpn, 0, tnum_quadrature_points, (const double *)dv, (const double *)da, (double *)du, 0));
+  PS_MUST(pspace_cuda_memcpy(UP, du, ub, 0));
+  pspace_cuda_free(dv); pspace_cuda_free(da); pspace_cuda_free(du);
+}
+
+void ParameterContainer::adjointProduct(int dvLen, scalar scale, const scalar *G, scalar *dfdx) {
+  ensureContext();
+  const size_t w = PSPACE_SCALAR_WIDTH;
+  const size_t gb = sizeof(double) * w * (size_t)tnum_quadrature_points * dvLen, db = sizeof(double) * w * (size_t)dvLen;
+  void *dg = 0, *dd = 0;
+  PS_MUST(pspace_cuda_malloc(&dg, gb));
+  PS_MUST(pspace_cuda_malloc(&dd, db));
+  PS_MUST(pspace_cuda_memcpy(dg, G, gb, 1));
+  PS_MUST(pspace_cuda_memcpy(dd, dfdx, db, 1));            // the reference adds into dfdx (:606-608)
+  PS_MUST(pspace_cuda_adjoint_product(ctx, dvLen, (const double *)&scale, 0, tnum_quadrature_points, (const double *)dg, (double *)dd, 1, 0));
+  PS_MUST(pspace_cuda_memcpy(dfdx, dd, db, 0));
+  pspace_cuda_free(dg); pspace_cuda_free(dd);
+}
+
 void ParameterContainer::projectVector(int m, const scalar *f, scalar *F) {
   ensureContext();
   pspace_project_args a;

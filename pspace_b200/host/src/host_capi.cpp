@@ -72,5 +72,11 @@ void pspace_host_project_matrix(void *c, int m2, const double *J, double *C) {
 void pspace_host_project_matrix_window(void *c, int m2, const double *J, int i0, int i1, int j0, int j1, double *C) {
   ((ParameterContainer *)c)->projectMatrixWindow(m2, reinterpret_cast<const scalar *>(J), i0, i1, j0, j1, reinterpret_cast<scalar *>(C));
 }
+void pspace_host_adjoint_states(void *c, int nnodes, int ndvpn, const double *v, const double *adj, double *UP) {
+  ((ParameterContainer *)c)->adjointStates(nnodes, ndvpn, reinterpret_cast<const scalar *>(v), reinterpret_cast<const scalar *>(adj), reinterpret_cast<scalar *>(UP));
+}
+void pspace_host_adjoint_product(void *c, int dvlen, const double *scale, const double *G, double *dfdx) {
+  ((ParameterContainer *)c)->adjointProduct(dvlen, *reinterpret_cast<const scalar *>(scale), reinterpret_cast<const scalar *>(G), reinterpret_cast<scalar *>(dfdx));
+}
 void *pspace_host_device_context(void *c) { return ((ParameterContainer *)c)->deviceContext(); }
 }

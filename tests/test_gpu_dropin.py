@@ -92,6 +92,17 @@ def test_host_library_against_golden(name):
     assert normwise(pc.projectVector(f), g["F"]) < 1e-12
     win = tuple(int(v) for v in g["win"])
     assert normwise(pc.projectMatrix(J, window=win), g["C"]) < 1e-12
+    # (f4) ParameterContainer::adjointStates / adjointProduct (host buffers) against the oracle's restatement of
+    # TACSStochasticElement::addAdjResProduct with the oracle's synthetic deterministic element
+    o = H.CpuContainer(H.oracle_api(cplx), golden_params(g), int(g["basis_type"])).initialize()
+    nnodes, ndvpn, dvlen, nv = 2, 2, 3, len(golden_params(g))
+    mm = nnodes * ndvpn
+    v, adj = syn(N * mm, seed + 5), syn(N * mm, seed + 6)
+    UP = pc.adjointStates(v, adj, nnodes, ndvpn)
+    U, P = UP[:, :mm], UP[:, mm:]
+    _, Yo, _ = o.grid()
+    G = np.stack([(P * U).sum(1) * (1.0 + 0.1 * n) + Yo[:, n % nv] * U.sum(1) for n in range(dvlen)], axis=1)
+    assert normwise(pc.adjointProduct(G, 0.5), o.adj_res_product(v, adj, nnodes, ndvpn, dvlen, 0.5)) < 1e-12
 
 
 DROPIN_SCRIPT = r'''

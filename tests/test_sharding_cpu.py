@@ -84,3 +84,29 @@ def test_two_rank_combine_gloo(cplx):
     assert all(r[1] < 1e-13 and r[2] < 1e-13 for r in res), res
     # the row blocks tile [0, N*N)
     assert res[0][3] == 0 and res[0][4] == res[1][3] and res[1][4] == res[1][5]
+
+
+def test_cabi_shard_rules_match_the_python_ones():
+    """C++ callers shard with pspace_cuda_shard_bounds / pspace_cuda_row_block (host arithmetic, no device needed); they must
+    cut the quadrature points and the basis rows exactly as pspace_b200.sharded does, so that mixed callers agree."""
+    import ctypes
+    from pspace_b200 import cabi
+    from pspace_b200.sharded import row_blocks, shard_bounds
+    L = ctypes.CDLL(cabi.LIB_PATH)
+    L.pspace_cuda_shard_bounds.argtypes = [ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong)]
+    L.pspace_cuda_row_block.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    for Q in (0, 1, 31, 32, 33, 64, 1000, 3125, 65536, 1048576, 1048577):
+        for world in (1, 2, 3, 4, 7, 8, 16):
+            ref = shard_bounds(Q, world) if Q > 0 else [(0, 0)] * world
+            for rank in range(world):
+                a, b = ctypes.c_longlong(), ctypes.c_longlong()
+                assert L.pspace_cuda_shard_bounds(Q, world, rank, ctypes.byref(a), ctypes.byref(b)) == 0
+                assert (a.value, b.value) == ref[rank], (Q, world, rank)
+    for rows in (0, 1, 5, 286, 1296):
+        for world in (1, 2, 3, 8):
+            ref = row_blocks(rows, world)
+            for rank in range(world):
+                r0, r1, per = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+                assert L.pspace_cuda_row_block(rows, world, rank, ctypes.byref(r0), ctypes.byref(r1), ctypes.byref(per)) == 0
+                assert (r0.value, r1.value) == ref[rank] and per.value == (rows + world - 1) // world
+    assert L.pspace_cuda_shard_bounds(10, 2, 2, None, None) != 0          # bad arguments are refused, not crashed on
