@@ -250,10 +250,11 @@ int pspace_cuda_memcpy(void *dst, const void *src, size_t bytes, int to_device);
 
 /* launches of this library's kernels since the context was created (bench "gpu_launches") */
 long long pspace_cuda_launch_count(const pspace_ctx *ctx);
-/* tuning / test switches.  "force_generic" = 1: use the all-warps cp.async projection kernel even where the
- * TMA warp-specialised kernel applies (the generic kernel is otherwise used only for operands TMA cannot
- * address: odd column counts or unaligned bases).  "panel_cache" = 0: rebuild the basis panels on every call.
- * "slab_mb" = n: upload slab size of the host-input forms. */
+/* tuning / test switches.  "force_generic": 0 (default) = the planner chooses between the TMA warp-specialised stream-K
+ * kernel and the single-launch cp.async kernel by size (matrix windows under ~1 GFLOP, and operands TMA cannot address
+ * - odd column counts, unaligned bases - take the single-launch kernel); 1 = always the single-launch kernel; -1 = the
+ * TMA kernel wherever it can run.  "force_panel" = 1: one-pass operators through the panel kernels.
+ * "panel_cache" = 0: rebuild the basis panels on every call.  "slab_mb" = n: upload slab size of the host-input forms. */
 int pspace_cuda_set_option(pspace_ctx *ctx, const char *name, int value);
 /* description + FLOP count of the kernel the last project call used */
 int pspace_cuda_last_plan(const pspace_ctx *ctx, char *buf, int buflen);

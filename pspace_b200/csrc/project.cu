@@ -33,6 +33,8 @@
 
 namespace {
 
+int sm_count(int device);
+
 constexpr int NT = 256;   // 8 warps
 constexpr int KQ = 32;    // quadrature points per pipeline stage (8 DMMA k-steps)
 constexpr int ZPAD = PSPACE_MAX_NQ;   // zero scalars appended to the staged tables (target of invalid rows)
@@ -56,6 +58,7 @@ struct ProjParams {
   int tiles_n, tiles_j, tiles_i;
   long long chunks_per_slice;
   int accumulate, vec16;
+  int fast;                 // host side only: 1 = TMA stream-K kernel, 0 = single-launch cp.async kernel
   double *sk_ws;           // stream-K partial tiles: [grid][2][BM*BN]   (fast path only)
   const unsigned char *mask;   // optional basis-pair filter [N][N] (matrix mode): 0 = structurally zero block
   int mask_ld;                 // = N
@@ -430,6 +433,7 @@ struct PanelParams {
   int r0, nr, nr_pad;       // basis rows [r0, r0+nr), panel row pitch nr_pad (pad rows are written as zeros)
   int weighted;
   int dsplit, tail_stride;  // variables [dsplit, nvars) are the "tail": tail_stride = prod of their rule sizes
+  int pts;                  // quadrature points per block (<= PSI_PTS; fewer for small grids, so that they still fill the machine)
   double *out;              // [width][q1-q0][nr_pad]
 };
 
@@ -447,10 +451,10 @@ __global__ void __launch_bounds__(PSI_MAXT) k_psi_panel(const __grid_constant__ 
   extern __shared__ __align__(16) unsigned char psm[];
   double *Ts = reinterpret_cast<double *>(psm);                        // 1-D tables, tsz scalars
   double *Ws = Ts + ((p.tsz * W + 1) & ~1);                            // weights of the block's points
-  uint8_t *Dg = reinterpret_cast<uint8_t *>(Ws + PSI_PTS * W);         // digit rows of the block's points [PSI_PTS][DP]
+  uint8_t *Dg = reinterpret_cast<uint8_t *>(Ws + PSI_PTS * W);         // digit rows of the block's points [pts][DP]
   const long long nq = p.q1 - p.q0;
-  const long long rb0 = blockIdx.x * (long long)PSI_PTS;
-  const int npts = (int)min((long long)PSI_PTS, nq - rb0);
+  const long long rb0 = blockIdx.x * (long long)p.pts;
+  const int npts = (int)min((long long)p.pts, nq - rb0);
   for (int i = threadIdx.x; i < p.tsz * W; i += blockDim.x) Ts[i] = p.T[i];
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(p.qdig + (p.q0 + rb0) * p.DP);
@@ -1016,7 +1020,13 @@ int ensure_panel(pspace_ctx *c, bool weighted, int r0, int nr, long long q0, lon
   pp.weighted = weighted ? 1 : 0; pp.out = s.d;
   const size_t smem = (size_t)(((c->tsz * W + 1) & ~1) + PSI_PTS * W) * 8 + (size_t)PSI_PTS * c->DP;
   const int nt = std::min(PSI_MAXT, (pp.nr_pad + 31) & ~31);
-  const dim3 grid((unsigned)((nq + PSI_PTS - 1) / PSI_PTS), (unsigned)((pp.nr_pad + nt - 1) / nt));
+  // points per block: 128 for big grids (long runs amortise the prefix products); small grids get shorter runs so that at
+  // least ~4 blocks per SM exist (cfg2: 3125 points x 126 rows was 25 blocks walking 128 points each: 35 us per panel)
+  const long long row_blocks = (pp.nr_pad + nt - 1) / nt;
+  int pts = PSI_PTS;
+  while (pts > 16 && ((nq + pts - 1) / pts) * row_blocks < 4LL * sm_count(c->device)) pts >>= 1;
+  pp.pts = pts;
+  const dim3 grid((unsigned)((nq + pts - 1) / pts), (unsigned)row_blocks);
   if (smem > 48 * 1024) {   // only then is an opt-in needed (tables of more than ~5000 entries); never on the BASELINE configs
     if (c->is_complex) PS_CUDA(cudaFuncSetAttribute(k_psi_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else PS_CUDA(cudaFuncSetAttribute(k_psi_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1074,7 +1084,7 @@ struct Plan {
 template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &pl, const pspace_project_args *a,
                                double *d_out, void *d_ws, cudaStream_t st) {
   pspace_ctx *mc = const_cast<pspace_ctx *>(c);
-  if (p.vec16 && !c->force_generic) {
+  if (p.fast) {
     typedef WsLayout<TL> LY;
     constexpr bool MAT = TL::MODE == MODE_MATRIX;
     const size_t smem = LY::smem_bytes();
@@ -1390,6 +1400,15 @@ int ps_project_ex(const pspace_ctx *c, int is_matrix, const pspace_project_args 
   p.tiles_n = pl.tiles_n; p.tiles_j = pl.tiles_j; p.tiles_i = pl.tiles_i;
   p.chunks_per_slice = pl.chunks_per_slice;
   p.vec16 = ((ncols_d % 2) == 0 && (reinterpret_cast<size_t>(d_in) % 16) == 0) ? 1 : 0;
+  // Kernel choice.  The TMA stream-K kernel needs a 16-byte addressable operand and costs two panel launches + a fix-up
+  // on top of its own; below ~1 GFLOP of window the single-launch kernel (basis values formed in the kernel) is faster
+  // (profiles/r02_small_problems.md: 64 x 64 x 64 points x 64 columns 14 us against 37 us).  force_generic: 1 = always
+  // the single-launch kernel, -1 = the TMA kernel wherever it can run (tests), 0 = by size.
+  p.fast = (p.vec16 && c->force_generic <= 0) ? 1 : 0;
+  if (p.fast && c->force_generic == 0 && !c->force_panel && !peer && !(is_matrix && a->symmetric)) {   // symmetric: keep the bitwise mirror
+    const double rows = is_matrix ? (double)(a->k1 - a->k0) * (a->j1 - a->j0) : (double)(a->k1 - a->k0);
+    if (2.0 * rows * (double)(a->q1 - a->q0) * ncols_d * c->width < 1e9) p.fast = 0;
+  }
   if (is_matrix) {
     p.i0 = a->k0; p.ni = a->k1 - a->k0; p.j0 = a->j0; p.nj = a->j1 - a->j0;
     p.stride_j = ncols_d; p.stride_i = (long long)p.nj * ncols_d;
@@ -1405,7 +1424,7 @@ int ps_project_ex(const pspace_ctx *c, int is_matrix, const pspace_project_args 
   if (peer) {
     if (!is_matrix || a->d_pair_mask || a->symmetric || a->accumulate)
       return ps_fail(PSPACE_EINVAL, "fused peer projection: matrix mode without mask / symmetric / accumulate");
-    if (!(p.vec16 && !c->force_generic)) return ps_fail(PSPACE_EINVAL, "fused peer projection needs a TMA-addressable operand (even column count, 16-byte aligned)");
+    if (!p.fast) return ps_fail(PSPACE_EINVAL, "fused peer projection needs a TMA-addressable operand (even column count, 16-byte aligned)");
     const Variant &pv = MAT_VARIANTS[pl.variant_idx];
     const int npt = pl.tiles_i * pl.tiles_j;
     p.peer_world = peer->world; p.peer_rank = peer->rank;
@@ -1417,7 +1436,7 @@ int ps_project_ex(const pspace_ctx *c, int is_matrix, const pspace_project_args 
     if (a->k0 != a->j0 || a->k1 != a->j1) return ps_fail(PSPACE_EINVAL, "symmetric projection needs a square window (i range == j range)");
     if (a->d_pair_mask) return ps_fail(PSPACE_EINVAL, "symmetric and d_pair_mask cannot be combined");
     // only the TMA kernel implements it; operands it cannot address take the dense generic kernel (same result)
-    p.symmetric = (p.vec16 && !c->force_generic) ? 1 : 0;
+    p.symmetric = p.fast;
   }
 
   const Variant &v = (is_matrix ? MAT_VARIANTS : VEC_VARIANTS)[pl.variant_idx];

@@ -250,7 +250,7 @@ def test_tma_and_generic_kernels_agree_with_oracle(cplx):
             J = J + 1j * rng.normal(size=J.shape)
         Jd = torch.from_numpy(J).cuda()
         ref = o.project_matrix(J, 5, 31, 90, 100, nthreads=8)
-        c.setOption("force_generic", 0)
+        c.setOption("force_generic", -1)
         C1 = c.projectMatrix(Jd, 5, 31, 90, 100).cpu().numpy()
         assert "tma" in c.lastPlan()
         c.setOption("force_generic", 1)
@@ -592,7 +592,7 @@ def test_masked_projection_sparsity_filter(cplx):
             Jd = torch.from_numpy(J).cuda()
             dense = o.project_matrix(J, nthreads=8)
             ref = dense * maskh[:, :, None]
-            for force in (0, 1):
+            for force in (-1, 0, 1):       # TMA kernel / planner's choice / single-launch kernel
                 c.setOption("force_generic", force)
                 got = c.projectMatrix(Jd, mask=mask).cpu().numpy()
                 assert normwise(got, ref) < TOL, (dmapf, m2, force)
@@ -708,7 +708,7 @@ def test_edge_shapes_vs_oracle(case):
     i1, j1 = min(o.N, 24), min(o.N, 40)
     ref = o.project_matrix(J, 0, i1, 0, j1, nthreads=8)
     tol = 5e-11 if case == "one_var_20pts" else TOL      # degree-19 Hermite at |z| ~ 7: values ~1e6, reference-order cancellation
-    for force in (0, 1):
+    for force in (-1, 0, 1):       # TMA kernel / planner's choice / single-launch kernel
         c.setOption("force_generic", force)
         assert normwise(c.projectMatrix(Jd, 0, i1, 0, j1).cpu().numpy(), ref) < tol, (case, force)
         assert normwise(c.projectVector(Jd).cpu().numpy(), o.project_vector(J)) < tol, (case, force)
@@ -750,7 +750,7 @@ def test_no_write_outside_the_output_window():
         J = torch.from_numpy(rng.normal(size=(Q, m2))).cuda()
         for (i0, i1, j0, j1) in ((0, N, 0, N), (3, 20, 5, 6), (N - 1, N, 0, N)):
             n = (i1 - i0) * (j1 - j0) * m2
-            for force in (0, 1):
+            for force in (-1, 0, 1):       # TMA kernel / planner's choice / single-launch kernel
                 c.setOption("force_generic", force)
                 for ks in (0, 2):
                     buf = torch.full((n + 2 * guard,), -7.25, dtype=torch.float64, device="cuda")
@@ -761,7 +761,7 @@ def test_no_write_outside_the_output_window():
                     assert not bool((out == -7.25).any())
         for (k0, k1) in ((0, N), (7, 9)):
             n = (k1 - k0) * m2
-            for force in (0, 1):
+            for force in (-1, 0, 1):       # TMA kernel / planner's choice / single-launch kernel
                 c.setOption("force_generic", force)
                 buf = torch.full((n + 2 * guard,), -7.25, dtype=torch.float64, device="cuda")
                 out = buf[guard:guard + n].view(k1 - k0, m2)
