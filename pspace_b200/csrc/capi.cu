@@ -430,6 +430,7 @@ long long pspace_cuda_launch_count(const pspace_ctx *c) { return c ? c->launches
 int pspace_cuda_set_option(pspace_ctx *c, const char *name, int value) {
   if (!c || !name) return ps_fail(PSPACE_EINVAL, "null argument");
   if (!strcmp(name, "force_generic")) { c->force_generic = value; return PSPACE_OK; }
+  if (!strcmp(name, "no_ragged")) { c->no_ragged = value; return PSPACE_OK; }
   if (!strcmp(name, "force_panel")) { c->force_panel = value; return PSPACE_OK; }
   if (!strcmp(name, "slab_mb")) { c->slab_bytes = value < 0 ? -((long long)(-value) << 20) : ((long long)value << 20); return PSPACE_OK; }
   if (!strcmp(name, "panel_cache")) { c->panel_cache = value; c->invalidate_panels(); return PSPACE_OK; }

@@ -542,7 +542,65 @@ __global__ void __launch_bounds__(PSI_MAXT) k_psi_panel(const __grid_constant__ 
 //              the rank that owns the tile (peer-mapped symmetric memory), overlapping the exchange with the math of
 //              the following tiles; k_peer_reduce_gather finishes the collective
 enum { EPI_DENSE = 0, EPI_MASKED = 1, EPI_PEER = 2 };
-template <class TL, int EPI>
+// k-steps [0, nks) of one stage, rolled: the last, partly filled chunk of a tile in the RAG instantiation of k_project_ws.
+// Same arithmetic, in the same order, as the unrolled loop of the kernel.
+template <class TL>
+__device__ __forceinline__ void ws_tail_ksteps(double (&acc)[TL::WM][TL::WN][2], const int nks, const double *bs, const double *bs2,
+                                               const double *pj, const double *pi, const int wgm, const int g, const int kl,
+                                               const unsigned sgn) {
+  typedef WsLayout<TL> LY;
+  constexpr int WM = TL::WM, WN = TL::WN, LDB = TL::LDB, BIP = TL::BIP, PJP = TL::PJP, KQ = LY::KQW;
+  constexpr bool CPLX = TL::CPLX, MAT = TL::MODE == MODE_MATRIX, PAIRED = CPLX && (WN % 2) == 0;
+#pragma unroll 1
+  for (int ks = 0; ks < nks; ks++) {
+    const int k = ks * 4 + kl;
+    double are[WM], aim[WM];
+    if (MAT) {
+      const double ajr = pj[k * PJP + g];
+      const double aji = CPLX ? pj[KQ * PJP + k * PJP + g] : 0.0;
+#pragma unroll
+      for (int a = 0; a < WM; a++) {
+        const double air = pi[k * BIP + wgm * WM + a];
+        if (!CPLX) are[a] = air * ajr;
+        else {
+          const double aii = pi[KQ * BIP + k * BIP + wgm * WM + a];
+          are[a] = air * ajr - aii * aji;
+          aim[a] = air * aji + aii * ajr;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < WM; a++) {
+        are[a] = pj[k * PJP + (wgm * WM + a) * 8 + g];
+        if (CPLX) aim[a] = pj[KQ * PJP + k * PJP + (wgm * WM + a) * 8 + g];
+      }
+    }
+    double bfr[WN], bsw[WN];
+    if (PAIRED) {
+#pragma unroll
+      for (int b2 = 0; b2 < WN / 2; b2++) {
+        const double2 v = *reinterpret_cast<const double2 *>(bs2 + k * LDB + 16 * b2);
+        bfr[2 * b2] = v.x; bfr[2 * b2 + 1] = v.y;
+        if (CPLX) { bsw[2 * b2] = flip_sign(v.y, 0x80000000u); bsw[2 * b2 + 1] = v.x; }
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < WN; b++) {
+        bfr[b] = bs[k * LDB + b * 8];
+        if (CPLX) bsw[b] = flip_sign(bs[k * LDB + b * 8 + ((g & 1) ? -1 : 1)], sgn);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < WM; a++)
+#pragma unroll
+      for (int b = 0; b < WN; b++) {
+        dmma884(acc[a][b][0], acc[a][b][1], are[a], bfr[b]);
+        if (CPLX) dmma884(acc[a][b][0], acc[a][b][1], aim[a], bsw[b]);
+      }
+  }
+}
+
+template <class TL, int EPI, bool RAG = false>
 __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__ ProjParams p,
                                                          const __grid_constant__ CUtensorMap tmapB,
                                                          const __grid_constant__ CUtensorMap tmapI,
@@ -645,6 +703,7 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
       if (PAIRED) { const int b2 = idx >> 1, e = idx & 1; v0 = ac[a][2 * b2][e]; v1 = ac[a][2 * b2 + (WN > 1 ? 1 : 0)][e]; cc = 16 * b2 + 4 * kl + 2 * e; }
       else { v0 = ac[a][idx][0]; v1 = ac[a][idx][1]; cc = 8 * idx + 2 * kl; }
     };
+    const int nks_last = (int)((p.q1 - p.q0 - (long long)(nchunk - 1) * KQ + 3) / 4);   // k-steps of a tile's last chunk that hold points
     int it = 0;
     for (int sidx = 0; sidx < nseg; sidx++) {
     int tile, c0, c1, slot;
@@ -657,7 +716,8 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
 #pragma unroll
       for (int b = 0; b < WN; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    for (int c = c0; c < c1; c++, it++) {
+    const int c1m = (RAG && c1 == nchunk) ? c1 - 1 : c1;     // RAG: the tile's last chunk is handled after the loop
+    for (int c = c0; c < c1m; c++, it++) {
       const int s = it % STAGES;
       const unsigned n = (unsigned)(it / STAGES);
       mbar_wait(&full[s], n & 1u);
@@ -666,6 +726,10 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
       const double *bs2 = reinterpret_cast<const double *>(st) + wgn * WN * 8 + 2 * g;
       const double *pj = reinterpret_cast<const double *>(st + LY::PJ_OFF);
       const double *pi = reinterpret_cast<const double *>(st + LY::PI_OFF);
+      // RAG instantiation (launched when the point count is not a multiple of the stage): the last chunk of a tile runs
+      // only the k-steps that hold points — the rows TMA zero-filled add exact zeros, so the result keeps its bits
+      // (cfg3: 1296 points = 20.25 stages, 3.6 % of the DMMAs were such zeros).  The tail is a separate rolled loop
+      // (ws_tail_ksteps) after the chunk loop so that the unrolled loop below, whose ptxas schedule is fragile, stays as it is.
 #pragma unroll
       for (int ks = 0; ks < KQ / 4; ks++) {
         const int k = ks * 4 + kl;
@@ -718,6 +782,17 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);      // see the producer: a stage is refilled one release LATER than this one
+    }
+    if (RAG && c1m < c1) {
+      const int s = it % STAGES;
+      mbar_wait(&full[s], (unsigned)(it / STAGES) & 1u);
+      const unsigned char *st = stage_base + (size_t)s * LY::STAGE_BYTES;
+      ws_tail_ksteps<TL>(acc, nks_last, reinterpret_cast<const double *>(st) + wgn * WN * 8 + g,
+                         reinterpret_cast<const double *>(st) + wgn * WN * 8 + 2 * g, reinterpret_cast<const double *>(st + LY::PJ_OFF),
+                         reinterpret_cast<const double *>(st + LY::PI_OFF), wgm, g, kl, sgn);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+      it++;
     }
 
     // ---- epilogue of this segment ----------------------------------------------------------------
@@ -1117,6 +1192,7 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
     if (!attr_ws.load(std::memory_order_acquire)) {
       PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       if (MAT) {
+        PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, EPI_DENSE, MAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, MAT ? EPI_MASKED : EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         PS_CUDA(cudaFuncSetAttribute(k_project_ws<TL, MAT ? EPI_PEER : EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       }
@@ -1125,6 +1201,9 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
     p.out = d_out;
     p.accumulate = a->accumulate;
     p.sk_ws = (double *)d_ws;
+    // dense matrix launches whose last stage is at most 3/4 full and is >= 0.4 % of a tile's k-loop: kernel with the trimmed last chunk
+    const long long tail_pts = (long long)(nq % LY::KQW);
+    const bool ragged = !c->no_ragged && tail_pts != 0 && tail_pts <= LY::KQW * 3 / 4 && (LY::KQW - tail_pts) * 250 >= (long long)nq;
     int fix_blocks = pl.sk_rem_tiles;
     int *d_list = nullptr;
     if (p.mask || p.symmetric) {
@@ -1141,6 +1220,7 @@ template <class TL> int launch(const pspace_ctx *c, ProjParams &p, const Plan &p
     }
     if (MAT && p.peer_world > 0) k_project_ws<TL, MAT ? EPI_PEER : EPI_DENSE><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
     else if (MAT && (p.mask || p.symmetric)) k_project_ws<TL, MAT ? EPI_MASKED : EPI_DENSE><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
+    else if (MAT && ragged) k_project_ws<TL, EPI_DENSE, MAT><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
     else k_project_ws<TL, EPI_DENSE><<<pl.sk_grid, NT_WS, smem, st>>>(p, tmB, tmI, tmJ);
     PS_LAUNCH_CHECK(c);
     if (fix_blocks > 0) {

@@ -267,6 +267,32 @@ def test_tma_and_generic_kernels_agree_with_oracle(cplx):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
+def test_trimmed_last_chunk_keeps_the_bits(cplx):
+    """Point counts that are not a multiple of the TMA stage: the dense matrix kernel skips the k-steps of the last chunk
+    that hold only zero-filled rows.  Adding those zeros changed nothing, so the output is bitwise the same as with the
+    full last chunk (option no_ragged), for whole tiles and for the stream-K remainder (partial tiles through the fix-up)."""
+    rng = np.random.default_rng(77)
+    ps = [("uniform", -1.0, 2.0, 5), ("normal", 0.5, 0.4, 5), ("exponential", 1.0, 0.3, 4)]      # N = Q = 180 = 2 x 64 + 52 ... 5 x 32 + 20
+    o = H.CpuContainer(H.oracle_api(cplx), ps, 0).initialize()
+    c = _dc(ps, 0, cplx).initialize()
+    c.setOption("force_generic", -1)
+    for m2, q1 in ((576, o.Q), (64, o.Q), (96, 77), (576, 145)):
+        J = rng.normal(size=(o.Q, m2)).astype(o.dtype)
+        if cplx:
+            J = J + 1j * rng.normal(size=J.shape)
+        Jd = torch.from_numpy(J).cuda()
+        c.setOption("no_ragged", 1)
+        full = c.projectMatrix(Jd[:q1], q0=0, q1=q1).clone()
+        c.setOption("no_ragged", 0)
+        trimmed = c.projectMatrix(Jd[:q1], q0=0, q1=q1)
+        assert "tma" in c.lastPlan()
+        assert torch.equal(full, trimmed), (m2, q1)
+        if q1 == o.Q:
+            assert normwise(trimmed[3:9, 100:].cpu().numpy(), o.project_matrix(J, 3, 9, 100, o.N, nthreads=8)) < TOL
+    c.close()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
 def test_expansion_evaluation_vs_oracle(cplx):
     """(f1) U[q][c] = sum_k psi_k(z_q) V[k][c] (getDeterministicStates), incl. ranges, odd columns, accumulate, and the
     round trip project(evaluate(V)) == V (orthonormality: exact quadrature of degree <= 2p)."""

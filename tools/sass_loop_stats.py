@@ -42,7 +42,13 @@ def main():
             continue
         tw = [i for i, x in enumerate(ins[: idx[0]]) if "TRYWAIT" in x[0]]
         start = tw[-1] if tw else idx[0]
-        loop = ins[start: idx[-1] + 1]
+        # the RAG instantiations carry a second, rolled loop (the trimmed last chunk) after the main one: the main loop is
+        # the first `main` DMMAs, the largest multiple of 64 (k-steps x 8x8 tiles of a 64-point stage)
+        main = len(idx) if len(idx) % 64 == 0 else (len(idx) // 64) * 64
+        if main == 0:
+            main = len(idx)
+        loop = ins[start: idx[main - 1] + 1]
+        idx = idx[:main]
         short = re.sub(r"_ZN\d+_GLOBAL__N__[0-9a-f_]+project_cu_[0-9a-f_]+", "", name)[:70]
         print(f"{short:70s} instrs {len(ins):5d}  loop {len(loop):4d}  DMMA {len(idx):4d}  static stall cycles/chunk {sum(x[1] for x in loop):5d}")
 
