@@ -254,7 +254,10 @@ long long pspace_cuda_launch_count(const pspace_ctx *ctx);
  * kernel and the single-launch cp.async kernel by size (matrix windows under ~1 GFLOP, and operands TMA cannot address
  * - odd column counts, unaligned bases - take the single-launch kernel); 1 = always the single-launch kernel; -1 = the
  * TMA kernel wherever it can run.  "force_panel" = 1: one-pass operators through the panel kernels.
- * "panel_cache" = 0: rebuild the basis panels on every call.  "slab_mb" = n: upload slab size of the host-input forms. */
+ * "panel_cache" = 0: rebuild the basis panels on every call.  "slab_mb" = n: upload slab size of the host-input forms.
+ * "out_block_mb" = n (default 256): pspace_cuda_project_matrix_host reads C back in blocks of basis rows of about n MB,
+ * overlapped with the projection of the next block, when J fits one upload slab and C is at least four blocks.
+ * "no_ragged" = 1: keep the full last TMA stage in the matrix kernel (A/B timing; same bits either way). */
 int pspace_cuda_set_option(pspace_ctx *ctx, const char *name, int value);
 /* description + FLOP count of the kernel the last project call used */
 int pspace_cuda_last_plan(const pspace_ctx *ctx, char *buf, int buflen);

@@ -308,7 +308,7 @@ static int ensure(void **buf, size_t *have, size_t need) {
 // double buffer — slab s+1 is uploaded on the copy stream while slab s is projected (accumulating into d_out) on the
 // compute stream — so only the first slab's upload is exposed and the device never holds more than two slabs of J.
 // Pinned host memory makes the uploads truly asynchronous; pageable memory works too (staged by the driver).
-static int project_hostin(pspace_ctx *c, int is_matrix, const pspace_project_args *a, const double *h_in, double *d_out) {
+static int ensure_streams(pspace_ctx *c) {
   PS_CUDA(cudaSetDevice(c->device));
   if (!c->own_stream) PS_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   if (!c->copy_stream) {
@@ -318,12 +318,22 @@ static int project_hostin(pspace_ctx *c, int is_matrix, const pspace_project_arg
       PS_CUDA(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
     }
   }
+  return PSPACE_OK;
+}
+
+static size_t slab_target(const pspace_ctx *c) {
+  return c->slab_bytes != 0 ? (size_t)(c->slab_bytes < 0 ? -c->slab_bytes : c->slab_bytes) : ((size_t)384 << 20);
+}
+
+static int project_hostin(pspace_ctx *c, int is_matrix, const pspace_project_args *a, const double *h_in, double *d_out) {
+  int rc0 = ensure_streams(c);
+  if (rc0) return rc0;
   cudaStream_t st = c->own_stream, cs = c->copy_stream;
   const size_t w = c->width;
   const long long nq = a->q1 - a->q0;
   const size_t row_bytes = sizeof(double) * w * a->ncols;
   const size_t in_bytes = row_bytes * (size_t)nq;
-  const size_t target = c->slab_bytes != 0 ? (size_t)(c->slab_bytes < 0 ? -c->slab_bytes : c->slab_bytes) : ((size_t)384 << 20);
+  const size_t target = slab_target(c);
   // slab sizes: the first upload is the only one not hidden behind a projection, so the slabs START small (1/16 of the
   // target) and double up to the target — the exposed copy shrinks 16x, the later slabs keep the kernel's stream-K waves long
   long long max_rows = (long long)((target + row_bytes - 1) / (row_bytes ? row_bytes : 1));
@@ -368,6 +378,48 @@ static int project_hostin(pspace_ctx *c, int is_matrix, const pspace_project_arg
   return PSPACE_OK;
 }
 
+// Output-bound matrix projections (cfg3: 6 MB of J in, 7.7 GB of C out per element): J is uploaded once and the window is
+// projected in blocks of basis rows i through two device buffers; block s is read back on the copy stream while block s+1 is
+// projected, so the call costs max(projection, read-back) + one block instead of their sum, and the device holds two blocks
+// of C instead of the whole window.  A row block is an ordinary window call on whole 16-row pair tiles.
+static int project_host_rowblocks(pspace_ctx *c, const pspace_project_args *a, const double *h_in, double *h_out) {
+  int rc = ensure_streams(c);
+  if (rc) return rc;
+  cudaStream_t st = c->own_stream, cs = c->copy_stream;
+  const size_t w = c->width;
+  const size_t in_bytes = sizeof(double) * w * a->ncols * (size_t)(a->q1 - a->q0);
+  const size_t row_out = sizeof(double) * w * (size_t)(a->j1 - a->j0) * a->ncols;      // bytes of C per basis row i
+  const int ni = a->k1 - a->k0;
+  int blk = (int)std::max<size_t>(16, c->out_block_bytes / row_out / 16 * 16);            // whole 16-row pair tiles
+  blk = std::min(blk, ni);
+  if ((rc = ensure(&c->d_scratch_in, &c->scratch_in_bytes, in_bytes))) return rc;
+  if ((rc = ensure(&c->d_scratch_out, &c->scratch_out_bytes, 2 * (size_t)blk * row_out))) return rc;
+  pspace_project_args as = *a;
+  as.k1 = a->k0 + blk;
+  size_t ws = ps_project_workspace(c, 1, &as);
+  if (ni % blk) { as.k0 = a->k0 + ni / blk * blk; as.k1 = a->k1; ws = std::max(ws, ps_project_workspace(c, 1, &as)); }
+  if ((rc = ensure(&c->d_scratch_ws, &c->scratch_ws_bytes, ws))) return rc;
+  PS_CUDA(cudaMemcpyAsync(c->d_scratch_in, h_in, in_bytes, cudaMemcpyHostToDevice, st));
+  int s = 0;
+  for (int r0 = 0; r0 < ni; r0 += blk, s++) {
+    const int b = s & 1, r1 = std::min(ni, r0 + blk);
+    double *buf = (double *)((unsigned char *)c->d_scratch_out + (size_t)b * blk * row_out);
+    unsigned char *hblk = (unsigned char *)h_out + (size_t)r0 * row_out;
+    if (s >= 2) PS_CUDA(cudaStreamWaitEvent(st, c->ev_copy[b], 0));                  // read-back of block s-2 has drained buffer b
+    if (a->accumulate) PS_CUDA(cudaMemcpyAsync(buf, hblk, (size_t)(r1 - r0) * row_out, cudaMemcpyHostToDevice, st));
+    as = *a;
+    as.k0 = a->k0 + r0; as.k1 = a->k0 + r1;
+    if ((rc = ps_project(c, 1, &as, (const double *)c->d_scratch_in, buf, c->d_scratch_ws, ws, st))) return rc;
+    PS_CUDA(cudaEventRecord(c->ev_comp[b], st));
+    PS_CUDA(cudaStreamWaitEvent(cs, c->ev_comp[b], 0));
+    PS_CUDA(cudaMemcpyAsync(hblk, buf, (size_t)(r1 - r0) * row_out, cudaMemcpyDeviceToHost, cs));
+    PS_CUDA(cudaEventRecord(c->ev_copy[b], cs));
+  }
+  PS_CUDA(cudaStreamSynchronize(st));
+  PS_CUDA(cudaStreamSynchronize(cs));
+  return PSPACE_OK;
+}
+
 static int project_host(pspace_ctx *c, int is_matrix, const pspace_project_args *a, const double *h_in, double *h_out) {
   if (!c || !a || !h_in || !h_out) return ps_fail(PSPACE_EINVAL, "null argument");
   PS_CUDA(cudaSetDevice(c->device));
@@ -376,6 +428,10 @@ static int project_host(pspace_ctx *c, int is_matrix, const pspace_project_args 
   const size_t rows = is_matrix ? (size_t)(a->k1 - a->k0) * (a->j1 - a->j0) : (size_t)(a->k1 - a->k0);
   const size_t out_bytes = sizeof(double) * w * rows * a->ncols;
   int rc;
+  // one upload slab of J and at least four output blocks: pipeline the read-back over blocks of basis rows
+  if (is_matrix && !a->symmetric && out_bytes >= 4 * c->out_block_bytes && a->k1 - a->k0 >= 64 &&
+      sizeof(double) * w * a->ncols * (size_t)(a->q1 - a->q0) <= slab_target(c))
+    return project_host_rowblocks(c, a, h_in, h_out);
   if ((rc = ensure(&c->d_scratch_out, &c->scratch_out_bytes, out_bytes))) return rc;
   if (!c->own_stream) PS_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   cudaStream_t st = c->own_stream;
@@ -430,6 +486,7 @@ long long pspace_cuda_launch_count(const pspace_ctx *c) { return c ? c->launches
 int pspace_cuda_set_option(pspace_ctx *c, const char *name, int value) {
   if (!c || !name) return ps_fail(PSPACE_EINVAL, "null argument");
   if (!strcmp(name, "force_generic")) { c->force_generic = value; return PSPACE_OK; }
+  if (!strcmp(name, "out_block_mb")) { c->out_block_bytes = (size_t)std::max(1, value) << 20; return PSPACE_OK; }
   if (!strcmp(name, "no_ragged")) { c->no_ragged = value; return PSPACE_OK; }
   if (!strcmp(name, "force_panel")) { c->force_panel = value; return PSPACE_OK; }
   if (!strcmp(name, "slab_mb")) { c->slab_bytes = value < 0 ? -((long long)(-value) << 20) : ((long long)value << 20); return PSPACE_OK; }

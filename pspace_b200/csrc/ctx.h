@@ -57,6 +57,7 @@ struct pspace_ctx {
   void invalidate_panels() { panel_u.valid = panel_w.valid = false; }
   int panel_cache = 1;                   // reuse a panel when the (row range, q-range) of a call repeats
   int force_panel = 0;                   // tests / bench: one-pass operators through the round-1 panel kernels
+  size_t out_block_bytes = (size_t)256 << 20;   // host-output matrix form: read-back block (option out_block_mb)
   int no_ragged = 0;                     // tests / A-B timing: keep the full last chunk in k_project_ws (see RAG there)
   int force_generic = 0;                 // tests: force the cp.async kernel even where TMA is usable
   double plan_flop = 0.0;

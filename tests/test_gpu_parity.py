@@ -672,6 +672,43 @@ def test_host_input_slab_pipeline(cplx):
 
 
 @pytest.mark.parametrize("cplx", [False, True])
+def test_host_output_row_block_pipeline(cplx):
+    """Output-bound host form (cfg3's shape: small J, large C): C is projected and read back in blocks of basis rows through two
+    device buffers.  Forced here with out_block_mb = 1: the device-form result (to summation order: the stream-K split of a
+    block differs from the whole window's), incl. a ragged last block, a row-offset
+    window, a pair mask, accumulate into pinned and pageable host buffers; the oracle pins a sub-window."""
+    rng = np.random.default_rng(83)
+    ps = [("normal", 0.2 + (1e-30j if cplx else 0), 0.8, 4), ("uniform", -1.0, 1.5, 5), ("exponential", 0.5, 0.7, 4)]
+    o = H.CpuContainer(H.oracle_api(cplx), ps, 0).initialize()          # N = Q = 150
+    c = _dc(ps, 0, cplx).initialize()
+    N, m2 = o.N, 96
+    J = rng.normal(size=(o.Q, m2)).astype(o.dtype)
+    if cplx:
+        J = J + 1j * rng.normal(size=J.shape)
+    Jd = torch.from_numpy(J).cuda()
+    c.setOption("out_block_mb", 1)            # row of C = 150 x 96 x 8 (16) B = 115 (230) kB -> blocks of 16 rows, 10 blocks, last one ragged
+    for (i0, i1, kw) in ((0, N, {}), (3, N - 2, {}), (0, N, {"mask": True})):
+        mask = c.pairMask([2] * len(ps)) if kw else None
+        ref = c.projectMatrix(Jd, i0, i1, 0, N, mask=mask)
+        a = c._args(i0, i1, 0, N, 0, o.Q, m2, False, 0, 0, mask, False)
+        host = torch.empty((i1 - i0, N, m2), dtype=Jd.dtype).pin_memory()
+        Jp = torch.from_numpy(J).pin_memory()
+        from pspace_b200.cabi import check
+        check(c.L.pspace_cuda_project_matrix_host(c.h, __import__("ctypes").byref(a), Jp.data_ptr(), host.data_ptr()))
+        assert normwise(host.numpy(), ref.cpu().numpy()) < 1e-13, (i0, i1, kw)
+        if mask is not None:
+            assert bool((host[mask[i0:i1].cpu() == 0] == 0).all())
+    full = c.projectMatrix(Jd).cpu().numpy()
+    assert normwise(full[40:52, 100:], o.project_matrix(J, 40, 52, 100, N, nthreads=8)) < TOL
+    got = c.projectMatrixHost(J)                                        # pageable numpy in / out
+    assert normwise(got, full) < 1e-13
+    acc = np.full((N, N, m2), 2.0, dtype=o.dtype)
+    c.projectMatrixHost(J, out=acc, accumulate=True)
+    assert normwise(acc, full + 2.0) < 1e-13
+    c.close()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
 def test_symmetric_projection_matches_dense(cplx):
     """symmetric=1 computes pairs j >= i only and mirrors: same full window as the dense projection (the mirrored
     half is bitwise equal to its source block), for full and sub-square windows, with accumulate."""
