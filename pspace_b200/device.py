@@ -156,6 +156,7 @@ class DeviceContainer:
 
     def _workspace(self, is_matrix, a):
         need = self.L.pspace_cuda_project_workspace(self.h, is_matrix, ctypes.byref(a))
+        self._last_ws_need = need                    # tests: bytes of the workspace the call may touch
         if need == 0:
             return None, 0
         if self._ws is None or self._ws.numel() < need:

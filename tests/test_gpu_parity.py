@@ -834,6 +834,68 @@ def test_no_write_outside_the_output_window():
     c.close()
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+def test_no_write_outside_workspace_or_expansion_output(cplx):
+    """Own bounds check, continued: (i) the caller-provided workspace is used only up to the size the query returned (stream-K
+    partials of the matrix and the factored vector kernels, q-split slices of the single-launch kernel); (ii) the expansion
+    kernels (factored and panel) write only rows q0..q1-1 of U; (iii) the host-output row-block path writes only C."""
+    rng = np.random.default_rng(33)
+    ps = [("uniform", -1.0, 2.0, 3), ("normal", 0.5 + (1e-30j if cplx else 0), 0.4, 4), ("exponential", 1.0, 0.3, 3), ("normal", 0.0, 1.0, 2)]
+    c = _dc(ps, 0, cplx).initialize()              # N = Q = 240
+    N, Q = c.N, c.Q
+    guard = 1 << 16
+
+    def rand(shape):
+        a = rng.normal(size=shape)
+        return torch.from_numpy(a + 1j * rng.normal(size=shape) if cplx else a).cuda()
+
+    import ctypes
+
+    def guarded(kind, a, fn, tag):
+        need = c.L.pspace_cuda_project_workspace(c.h, kind, ctypes.byref(a))
+        c._ws = torch.full((need + (1 << 20),), 0xA5, dtype=torch.uint8, device="cuda")
+        fn()
+        torch.cuda.synchronize()
+        assert c._last_ws_need == need and bool((c._ws[need:] == 0xA5).all()), tag
+
+    for m2 in (24, 64, 576):
+        J = rand((Q, m2))
+        for force in (-1, 0, 1):
+            c.setOption("force_generic", force)
+            for ks in (0, 3):
+                for (q0, q1) in ((0, Q), (17, 203)):
+                    Jq = J[q0:q1].contiguous()
+                    guarded(1, c._args(0, 40, 3, N, q0, q1, m2, False, ks, 0),
+                            lambda: c.projectMatrix(Jq, 0, 40, 3, N, q0=q0, q1=q1, ksplit=ks), ("matrix", m2, force, ks, q0))
+                    guarded(0, c._args(0, N, 0, 0, q0, q1, m2, False, ks, 0),
+                            lambda: c.projectVector(Jq, 0, N, q0=q0, q1=q1, ksplit=ks), ("vector", m2, force, ks, q0))
+    c.setOption("force_generic", 0)
+    sent = -7.25
+    for m in (3, 24, 50):
+        V = rand((N, m))
+        for panel in (0, 1):
+            c.setOption("force_panel", panel)
+            for (q0, q1) in ((0, Q), (5, 6), (31, 222)):
+                n = (q1 - q0) * m
+                buf = torch.full((n + 2 * guard,), sent, dtype=V.dtype, device="cuda")
+                out = buf[guard:guard + n].view(q1 - q0, m)
+                c.evaluateExpansion(V, q0=q0, q1=q1, out=out)
+                torch.cuda.synchronize()
+                assert bool((buf[:guard] == sent).all()) and bool((buf[guard + n:] == sent).all()), (m, panel, q0, q1)
+                assert not bool((out == sent).any())
+    c.setOption("force_panel", 0)
+    # host-output row blocks: C inside a larger pinned buffer of sentinels
+    c.setOption("out_block_mb", 1)
+    m2 = 64
+    Jh = rand((Q, m2)).cpu().pin_memory()
+    n = N * N * m2
+    hbuf = torch.full((n + 2 * guard,), sent, dtype=Jh.dtype).pin_memory()
+    hout = hbuf[guard:guard + n].view(N, N, m2)
+    c.projectMatrixHost(Jh, out=hout)
+    assert bool((hbuf[:guard] == sent).all()) and bool((hbuf[guard + n:] == sent).all()) and not bool((hout == sent).any())
+    c.close()
+
+
 def test_error_paths_are_loud():
     from pspace_b200.cabi import PspaceCudaError
     ps = [("normal", 0.0, 1.0, 2)]
