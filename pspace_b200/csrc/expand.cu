@@ -313,17 +313,21 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
     int s = 0;
     unsigned ph = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int tn = (int)(tile % p.tiles_n);
-      const long long tq = tile / p.tiles_n;
+      const long long tq = p.tiles_n == 1 ? tile : tile / p.tiles_n;
+      const int tn = (int)(tile - tq * p.tiles_n);
       const long long qt0 = p.q0 + tq * BQ, blk0 = qt0 / p.L;
       int soff[WM], poff[WM];
+      {
+        // 32-bit index arithmetic relative to the tile's first prefix block (one 64-bit division per tile, above)
+        const int r0 = (int)(qt0 - blk0 * p.L);                      // tile's first point within its block
+        const int rmax = (int)min((long long)BQ - 1, p.q1 - 1 - qt0);   // rows past the range are computed on a valid point and not stored
 #pragma unroll
-      for (int a = 0; a < WM; a++) {
-        long long qa = qt0 + warp * (WM * 8) + a * 8 + g;
-        if (qa >= p.q1) qa = p.q1 - 1;                               // rows past the range are computed on a valid point and not stored
-        const long long b = qa / p.L;
-        soff[a] = (int)(qa - b * p.L) * spitch + kl;
-        poff[a] = (int)(b - blk0) * KCP + kl;
+        for (int a = 0; a < WM; a++) {
+          const int r = r0 + min(warp * (WM * 8) + a * 8 + g, rmax);
+          const int b = r / p.L;
+          soff[a] = (r - b * p.L) * spitch + kl;
+          poff[a] = b * KCP + kl;
+        }
       }
       double acc[WM][WN][2];
 #pragma unroll
@@ -341,8 +345,7 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
         const double *Pr = reinterpret_cast<const double *>(st + P_OFF), *Pi = Pr + (size_t)p.npfx * KCP;
         const int ksteps = (min(KC, p.nk - kc * KC) + 3) >> 2;
         int depi = 0;
-#pragma unroll 4
-        for (int ks = 0; ks < ksteps; ks++) {
+        auto kstep = [&](const int ks) {
           double are[WM], aim[WM];
 #pragma unroll
           for (int a = 0; a < WM; a++) {
@@ -377,6 +380,13 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
               if (CPLX) dmma884(acc[a][b][0], acc[a][b][1], aim[a], bsw[b]);
             }
           depi = __double2loint(are[WM - 1]) ^ __double2loint(bfr[WN - 1]);
+        };
+        if (ksteps == KC / 4) {
+#pragma unroll
+          for (int ks = 0; ks < KC / 4; ks++) kstep(ks);      // full chunk: one straight-line block, loads hoisted across k-steps
+        } else {
+#pragma unroll 2
+          for (int ks = 0; ks < ksteps; ks++) kstep(ks);
         }
         // release the stage: the arrive's address depends on the last fragment registers read from it
         const unsigned dep = (unsigned)depi & p.zero;
@@ -505,21 +515,27 @@ int ps_expand(const pspace_ctx *c, int k0, int k1, long long q0, long long q1, i
     if (z && wn == 3) wn = 4;       // complex tiles hold whole (re,im) pairs: even WN
     if (z && wn == 1) wn = 2;
     // stage rows KC: the candidate whose best factorisation loads the producers least (ties: the larger stage)
-#define PS_XF(WN_, Z_)                                                                                        \
+#define PS_XF(WM_, WN_, Z_)                                                                                   \
   {                                                                                                            \
-    const XFChoice a128 = plan_expand_f<XTile<4, WN_, Z_, 128>>(c, f.nk), a64 = plan_expand_f<XTile<4, WN_, Z_, 64>>(c, f.nk), \
-                   a32 = plan_expand_f<XTile<4, WN_, Z_, 32>>(c, f.nk);                                       \
+    const XFChoice a128 = plan_expand_f<XTile<WM_, WN_, Z_, 128>>(c, f.nk), a64 = plan_expand_f<XTile<WM_, WN_, Z_, 64>>(c, f.nk), \
+                   a32 = plan_expand_f<XTile<WM_, WN_, Z_, 32>>(c, f.nk);                                     \
     if (a128.ds >= 0 && (a64.ds < 0 || a128.score <= a64.score) && (a32.ds < 0 || a128.score <= a32.score))    \
-      return launch_expand_f<XTile<4, WN_, Z_, 128>>(c, f, d_V, st);                                           \
-    if (a64.ds >= 0 && (a32.ds < 0 || a64.score <= a32.score)) return launch_expand_f<XTile<4, WN_, Z_, 64>>(c, f, d_V, st); \
-    return launch_expand_f<XTile<4, WN_, Z_, 32>>(c, f, d_V, st);                                              \
+      return launch_expand_f<XTile<WM_, WN_, Z_, 128>>(c, f, d_V, st);                                         \
+    if (a64.ds >= 0 && (a32.ds < 0 || a64.score <= a32.score)) return launch_expand_f<XTile<WM_, WN_, Z_, 64>>(c, f, d_V, st); \
+    return launch_expand_f<XTile<WM_, WN_, Z_, 32>>(c, f, d_V, st);                                            \
   }
+    // narrow real tiles (<= 24 columns) take 512 points per CTA when that still gives every SM two tiles: the per-tile
+    // prologue/epilogue, where all eight consumer warps leave the tensor pipe idle together, is paid half as often and a
+    // V fragment feeds 8 row tiles instead of 4 (cfg5: 0.510 -> see profiles/r02_ops.md)
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+    const bool tall = !z && wn <= 3 && (q1 - q0) >= 2LL * nsm * 512;
     switch (wn) {
-      case 6: if (z) PS_XF(6, true) else PS_XF(6, false)
-      case 4: if (z) PS_XF(4, true) else PS_XF(4, false)
-      case 3: PS_XF(3, false)
-      case 2: if (z) PS_XF(2, true) else PS_XF(2, false)
-      default: PS_XF(1, false)
+      case 6: if (z) PS_XF(4, 6, true) else PS_XF(4, 6, false)
+      case 4: if (z) PS_XF(4, 4, true) else PS_XF(4, 4, false)
+      case 3: if (tall) PS_XF(8, 3, false) else PS_XF(4, 3, false)
+      case 2: if (z) PS_XF(4, 2, true) else if (tall) PS_XF(8, 2, false) else PS_XF(4, 2, false)
+      default: if (tall) PS_XF(8, 1, false) else PS_XF(4, 1, false)
     }
 #undef PS_XF
   }
