@@ -435,6 +435,7 @@ struct PanelParams {
   int dsplit, tail_stride;  // variables [dsplit, nvars) are the "tail": tail_stride = prod of their rule sizes
   int pts;                  // quadrature points per block (<= PSI_PTS; fewer for small grids, so that they still fill the machine)
   double *out;              // [width][q1-q0][nr_pad]
+  double *out_w;            // not null: `out` gets the unweighted panel and out_w the weighted one (same rows) in one pass
 };
 
 // Basis panel P[part][q][row] = psi_row(z_q) (x w_q when weighted), product order ((1*T_0)*T_1)*... as everywhere.
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(PSI_MAXT) k_psi_panel(const __grid_constant__ 
     const uint4 *src = reinterpret_cast<const uint4 *>(p.qdig + (p.q0 + rb0) * p.DP);
     uint4 *dst = reinterpret_cast<uint4 *>(Dg);
     for (int i = threadIdx.x; i < npts * (p.DP / 16); i += blockDim.x) dst[i] = src[i];
-    if (p.weighted)
+    if (p.weighted || p.out_w)
       for (int i = threadIdx.x; i < npts * W; i += blockDim.x) Ws[i] = p.W[(p.q0 + rb0) * W + i];
   }
   __syncthreads();
@@ -520,7 +521,12 @@ __global__ void __launch_bounds__(PSI_MAXT) k_psi_panel(const __grid_constant__ 
         }
       }
     }
-    if (p.weighted) {
+    if (!live) { vr = 0.0; vi = 0.0; }
+    if (p.out_w) {                  // both panels of a square window: the unweighted value goes out before the weight is applied
+      out_re[(size_t)t * p.nr_pad] = vr;
+      if (CPLX) out_im[(size_t)t * p.nr_pad] = vi;
+    }
+    if (p.weighted || p.out_w) {
       if (!CPLX) vr *= Ws[t];
       else {
         const double wre = Ws[2 * t], wim = Ws[2 * t + 1];
@@ -529,8 +535,9 @@ __global__ void __launch_bounds__(PSI_MAXT) k_psi_panel(const __grid_constant__ 
       }
     }
     if (!live) { vr = 0.0; vi = 0.0; }
-    out_re[(size_t)t * p.nr_pad] = vr;
-    if (CPLX) out_im[(size_t)t * p.nr_pad] = vi;
+    double *o_re = p.out_w ? p.out_w + (out_re - p.out) : out_re;
+    o_re[(size_t)t * p.nr_pad] = vr;
+    if (CPLX) { double *o_im = p.out_w ? p.out_w + (out_im - p.out) : out_im; o_im[(size_t)t * p.nr_pad] = vi; }
   }
 }
 
@@ -1061,12 +1068,14 @@ int make_tmap(CUtensorMap *tm, const double *base, int rank, const unsigned long
 
 // One basis panel (rows [r0, r0+nr) over [q0,q1), weighted or not) in its context slot: grow-only buffer, rebuilt
 // unless the cache is on and the slot already holds exactly this panel.
-int ensure_panel(pspace_ctx *c, bool weighted, int r0, int nr, long long q0, long long q1, double **d_out, int *nr_pad,
-                 cudaStream_t st) {
+// slot_prepare: buffer of the slot (grown if needed), ordered after its last use; *build = the panel has to be (re)written.
+int slot_prepare(pspace_ctx *c, bool weighted, int r0, int nr, long long q0, long long q1, double **d_out, int *nr_pad,
+                 cudaStream_t st, bool *build) {
   pspace_ctx::PanelSlot &s = weighted ? c->panel_w : c->panel_u;
   const int W = c->width;
   const long long nq = q1 - q0;
   *nr_pad = (nr + 1) & ~1;
+  *build = false;
   const size_t need = (size_t)W * nq * *nr_pad * 8;
   // order this call after the last use of the slot on whatever stream that was
   if (s.ev_pending) PS_CUDA(cudaStreamWaitEvent(st, s.ev, 0));
@@ -1085,14 +1094,24 @@ int ensure_panel(pspace_ctx *c, bool weighted, int r0, int nr, long long q0, lon
   if (need == 0) return PSPACE_OK;
   if (c->panel_cache && s.valid && s.r0 == r0 && s.nr == nr && s.q0 == q0 && s.q1 == q1) return PSPACE_OK;
   s.valid = false;
+  *build = true;
+  return PSPACE_OK;
+}
+
+// One launch of k_psi_panel for rows [r0, r0+nr) over [q0,q1): the unweighted panel into d_u and/or the weighted one into d_w.
+int panel_launch(pspace_ctx *c, int r0, int nr, long long q0, long long q1, double *d_u, double *d_w, cudaStream_t st) {
+  const int W = c->width;
+  const long long nq = q1 - q0;
   PanelParams pp;
   pp.nvars = c->nvars; pp.tsz = c->tsz; pp.DP = c->DP; pp.width = W;
   pp.T = c->d_T; pp.deg = c->d_deg; pp.qdig = c->d_qdig; pp.W = c->d_W;
   for (int d = 0; d < c->nvars; d++) { pp.toff[d] = c->toff[d]; pp.nq[d] = c->nq[d]; }
   pp.q0 = q0; pp.q1 = q1;
   ps_choose_tail(c, PSI_TAIL, &pp.dsplit, &pp.tail_stride);
-  pp.r0 = r0; pp.nr = nr; pp.nr_pad = *nr_pad;
-  pp.weighted = weighted ? 1 : 0; pp.out = s.d;
+  pp.r0 = r0; pp.nr = nr; pp.nr_pad = (nr + 1) & ~1;
+  pp.weighted = (d_w && !d_u) ? 1 : 0;
+  pp.out = d_u ? d_u : d_w;
+  pp.out_w = (d_u && d_w) ? d_w : nullptr;
   const size_t smem = (size_t)(((c->tsz * W + 1) & ~1) + PSI_PTS * W) * 8 + (size_t)PSI_PTS * c->DP;
   const int nt = std::min(PSI_MAXT, (pp.nr_pad + 31) & ~31);
   // points per block: 128 for big grids (long runs amortise the prefix products); small grids get shorter runs so that at
@@ -1109,8 +1128,24 @@ int ensure_panel(pspace_ctx *c, bool weighted, int r0, int nr, long long q0, lon
   if (c->is_complex) k_psi_panel<true><<<grid, nt, smem, st>>>(pp);
   else k_psi_panel<false><<<grid, nt, smem, st>>>(pp);
   PS_LAUNCH_CHECK(c);
+  return PSPACE_OK;
+}
+
+void slot_commit(pspace_ctx *c, bool weighted, int r0, int nr, long long q0, long long q1) {
+  pspace_ctx::PanelSlot &s = weighted ? c->panel_w : c->panel_u;
   s.r0 = r0; s.nr = nr; s.q0 = q0; s.q1 = q1;
   s.valid = true;
+}
+
+// One basis panel (rows [r0, r0+nr) over [q0,q1), weighted or not) in its context slot: grow-only buffer, rebuilt
+// unless the cache is on and the slot already holds exactly this panel.
+int ensure_panel(pspace_ctx *c, bool weighted, int r0, int nr, long long q0, long long q1, double **d_out, int *nr_pad,
+                 cudaStream_t st) {
+  bool build = false;
+  int rc = slot_prepare(c, weighted, r0, nr, q0, q1, d_out, nr_pad, st, &build);
+  if (rc || !build) return rc;
+  if ((rc = panel_launch(c, r0, nr, q0, q1, weighted ? nullptr : *d_out, weighted ? *d_out : nullptr, st))) return rc;
+  slot_commit(c, weighted, r0, nr, q0, q1);
   return PSPACE_OK;
 }
 
@@ -1119,11 +1154,21 @@ int build_panels(pspace_ctx *c, const ProjParams &p, bool matrix, double **d_pi,
                  int *nj_pad, cudaStream_t st) {
   *ni_pad = 0;
   *d_pi = nullptr;
-  if (matrix) {
-    int rc = ensure_panel(c, false, p.i0, p.ni, p.q0, p.q1, d_pi, ni_pad, st);
-    if (rc) return rc;
+  if (!matrix) return ensure_panel(c, true, p.j0, p.nj, p.q0, p.q1, d_pj, nj_pad, st);
+  bool bi = false, bj = false;
+  int rc = slot_prepare(c, false, p.i0, p.ni, p.q0, p.q1, d_pi, ni_pad, st, &bi);
+  if (rc) return rc;
+  if ((rc = slot_prepare(c, true, p.j0, p.nj, p.q0, p.q1, d_pj, nj_pad, st, &bj))) return rc;
+  if (bi && bj && p.i0 == p.j0 && p.ni == p.nj) {
+    // square window (the reference's all-pairs loop): both panels hold the same rows - one pass writes psi and w*psi
+    if ((rc = panel_launch(c, p.i0, p.ni, p.q0, p.q1, *d_pi, *d_pj, st))) return rc;
+  } else {
+    if (bi && (rc = panel_launch(c, p.i0, p.ni, p.q0, p.q1, *d_pi, nullptr, st))) return rc;
+    if (bj && (rc = panel_launch(c, p.j0, p.nj, p.q0, p.q1, nullptr, *d_pj, st))) return rc;
   }
-  return ensure_panel(c, true, p.j0, p.nj, p.q0, p.q1, d_pj, nj_pad, st);
+  if (bi) slot_commit(c, false, p.i0, p.ni, p.q0, p.q1);
+  if (bj) slot_commit(c, true, p.j0, p.nj, p.q0, p.q1);
+  return PSPACE_OK;
 }
 
 // sums the ksplit partial windows in slice order (deterministic) into the output
