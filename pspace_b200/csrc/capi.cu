@@ -400,21 +400,32 @@ static int project_host_rowblocks(pspace_ctx *c, const pspace_project_args *a, c
   if (ni % blk) { as.k0 = a->k0 + ni / blk * blk; as.k1 = a->k1; ws = std::max(ws, ps_project_workspace(c, 1, &as)); }
   if ((rc = ensure(&c->d_scratch_ws, &c->scratch_ws_bytes, ws))) return rc;
   PS_CUDA(cudaMemcpyAsync(c->d_scratch_in, h_in, in_bytes, cudaMemcpyHostToDevice, st));
-  int s = 0;
+  // Block s is projected BEFORE the read-back of block s-1 is issued: with pinned host memory both are asynchronous anyway;
+  // with pageable memory cudaMemcpyAsync holds the host thread until the copy is staged, and this order keeps the GPU busy
+  // with block s meanwhile.
+  auto read_back = [&](int sb, int r0, int r1) -> int {
+    const int b = sb & 1;
+    double *buf = (double *)((unsigned char *)c->d_scratch_out + (size_t)b * blk * row_out);
+    PS_CUDA(cudaStreamWaitEvent(cs, c->ev_comp[b], 0));
+    PS_CUDA(cudaMemcpyAsync((unsigned char *)h_out + (size_t)r0 * row_out, buf, (size_t)(r1 - r0) * row_out, cudaMemcpyDeviceToHost, cs));
+    PS_CUDA(cudaEventRecord(c->ev_copy[b], cs));
+    return PSPACE_OK;
+  };
+  int s = 0, prev_r0 = 0, prev_r1 = 0;
   for (int r0 = 0; r0 < ni; r0 += blk, s++) {
     const int b = s & 1, r1 = std::min(ni, r0 + blk);
     double *buf = (double *)((unsigned char *)c->d_scratch_out + (size_t)b * blk * row_out);
-    unsigned char *hblk = (unsigned char *)h_out + (size_t)r0 * row_out;
     if (s >= 2) PS_CUDA(cudaStreamWaitEvent(st, c->ev_copy[b], 0));                  // read-back of block s-2 has drained buffer b
-    if (a->accumulate) PS_CUDA(cudaMemcpyAsync(buf, hblk, (size_t)(r1 - r0) * row_out, cudaMemcpyHostToDevice, st));
+    if (a->accumulate)
+      PS_CUDA(cudaMemcpyAsync(buf, (unsigned char *)h_out + (size_t)r0 * row_out, (size_t)(r1 - r0) * row_out, cudaMemcpyHostToDevice, st));
     as = *a;
     as.k0 = a->k0 + r0; as.k1 = a->k0 + r1;
     if ((rc = ps_project(c, 1, &as, (const double *)c->d_scratch_in, buf, c->d_scratch_ws, ws, st))) return rc;
     PS_CUDA(cudaEventRecord(c->ev_comp[b], st));
-    PS_CUDA(cudaStreamWaitEvent(cs, c->ev_comp[b], 0));
-    PS_CUDA(cudaMemcpyAsync(hblk, buf, (size_t)(r1 - r0) * row_out, cudaMemcpyDeviceToHost, cs));
-    PS_CUDA(cudaEventRecord(c->ev_copy[b], cs));
+    if (s > 0 && (rc = read_back(s - 1, prev_r0, prev_r1))) return rc;
+    prev_r0 = r0; prev_r1 = r1;
   }
+  if (s > 0 && (rc = read_back(s - 1, prev_r0, prev_r1))) return rc;
   PS_CUDA(cudaStreamSynchronize(st));
   PS_CUDA(cudaStreamSynchronize(cs));
   return PSPACE_OK;
