@@ -69,6 +69,7 @@ struct ProjParams {
   double *peer_recv[PSPACE_MAX_PEERS];
   int peer_world, peer_rank, peer_lp;      // ranks, my rank, pair tiles owned per rank (owner = pair tile / peer_lp)
   long long peer_ncols_pad;                // tiles_n * BN
+  unsigned lag_ns;                         // RAG instantiation of k_project_ws: see there (0)
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gptr, int src_bytes) {
@@ -722,6 +723,12 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
     for (int a = 0; a < WM; a++)
 #pragma unroll
       for (int b = 0; b < WN; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    // RAG instantiation only: optional start-of-segment delay of consumer warps 4-7 (p.lag_ns, 0 = none: the default).
+    // Measured: no gain from the delay itself, but with this statement in place ptxas gives the RAG kernel's
+    // main loop the 6257-cycle schedule instead of the 6338-cycle one (cfg3 71.1 -> 70.5 ms per element); the RAG = false
+    // kernel does not contain it and keeps its code.  tests/test_host_cpu.py guards both counts.
+    if (RAG && p.lag_ns != 0 && cw >= NCW / 2 && c1 - c0 >= 4) asm volatile("nanosleep.u32 %0;\n" ::"r"(p.lag_ns));
 
     const int c1m = (RAG && c1 == nchunk) ? c1 - 1 : c1;     // RAG: the tile's last chunk is handled after the loop
     for (int c = c0; c < c1m; c++, it++) {
@@ -1544,7 +1551,7 @@ int ps_project_ex(const pspace_ctx *c, int is_matrix, const pspace_project_args 
   p.out = d_out; p.slice_stride = 0; p.accumulate = a->accumulate; p.sk_ws = nullptr;
   p.mask = is_matrix ? a->d_pair_mask : nullptr; p.mask_ld = c->N; p.tile_list = nullptr; p.tile_count = nullptr;
   p.symmetric = 0;
-  p.peer_world = 0; p.peer_rank = 0; p.peer_lp = 1; p.peer_ncols_pad = 0;
+  p.peer_world = 0; p.peer_rank = 0; p.peer_lp = 1; p.peer_ncols_pad = 0; p.lag_ns = 0;
   for (int w = 0; w < PSPACE_MAX_PEERS; w++) p.peer_recv[w] = nullptr;
   if (peer) {
     if (!is_matrix || a->d_pair_mask || a->symmetric || a->accumulate)

@@ -186,12 +186,12 @@ def test_dense_dmma_loop_keeps_the_fast_ptxas_schedule():
     assert m, out
     assert int(m.group(1)) == 384                      # 16 k-steps (64-point stage) x 2 row tiles x 12 column tiles
     assert int(m.group(2)) <= 6290, out                # 384 x 16 = 6144 is the floor; 6256 today (the slower schedule: >= 6300)
-    # the instantiation with the trimmed last chunk (point counts off the stage size, cfg3) gets the slower schedule for
-    # its main loop (6338): it trades 1.3 % there for the 3.6 % of zero k-steps it skips.  Guard against worse.
+    # the instantiation with the trimmed last chunk (point counts off the stage size, cfg3): 6338 as first written, 6257 with
+    # the (inactive) start-of-segment lag statement that only this instantiation contains (cfg3 71.1 -> 70.6 ms per element)
     out = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "sass_loop_stats.py"),
                                    "Li2ELi12ELi8ELi1ELb0ELi0ELi4ELi1EEELi0ELb1E"], text=True)
     m = re.search(r"DMMA\s+(\d+)\s+static stall cycles/chunk\s+(\d+)", out)
-    assert m and int(m.group(1)) == 384 and int(m.group(2)) <= 6400, out
+    assert m and int(m.group(1)) == 384 and int(m.group(2)) <= 6290, out
 
 
 def test_cpp_caller_example_builds_against_the_reference_headers():
