@@ -440,41 +440,55 @@ __global__ void __launch_bounds__(TL::NT, 1) k_project_vf(const __grid_constant_
 // Adds the stream-K pieces of each remainder tile and stores the tile.  grid = (remainder tiles, element slices); a block
 // owns 64 elements x 4 piece lanes: lane j adds the pieces j, j+4, j+8, ... in CTA order and the four partial sums are
 // combined as (s0 + s1) + (s2 + s3) — a fixed order, so the result is reproducible run to run.
-constexpr int VFX_ELEMS = 64;
+constexpr int VFX_ELEMS = 32, VFX_LANES = 256 / VFX_ELEMS;
 __global__ void __launch_bounds__(256) k_vfixup(const __grid_constant__ VParams p, int G, int BM, int BN) {
   const SkWork wk(G, p.tiles_r * p.tiles_n, p.nchunk);
   const int rt = blockIdx.x, tile = wk.nfull * G + rt;
   const int tn = tile % p.tiles_n, tr = tile / p.tiles_n;
   const long long u0 = (long long)rt * wk.nchunk, u1 = u0 + wk.nchunk;
   __shared__ int s_src[1024];
+  __shared__ short s_flag[1024];     // per CTA of the projection: 0 = no piece of this tile, 1 = its slot 0, 2 = its slot 1
   __shared__ int s_n;
-  __shared__ double part[4][VFX_ELEMS];
-  if (threadIdx.x == 0) {
-    // first CTA whose range reaches past u0, then every CTA until the ranges leave the tile
-    int g = (int)((u0 * G) / (wk.rem_units > 0 ? wk.rem_units : 1));
-    while (g > 0 && wk.lo(g) > u0) g--;
-    while (g < G && wk.lo(g + 1) <= u0) g++;
-    int n = 0;
-    for (; g < G && n < 1024; g++) {
-      const long long a0 = wk.lo(g), a1 = wk.lo(g + 1);
-      if (a0 >= u1) break;
-      if (a1 <= a0) continue;
-      s_src[n++] = g * 2 + ((a0 / wk.nchunk == rt) ? 0 : 1);
+  __shared__ double part[VFX_LANES][VFX_ELEMS];
+  // pieces of this tile: every thread tests CTAs (one 64-bit division each, in parallel); thread 0 then compacts the flags in
+  // CTA order, which fixes the order of the sum (the serial search with two divisions per step took most of this kernel's time)
+  for (int g = threadIdx.x; g < G && g < 1024; g += blockDim.x) {
+    const long long a0 = wk.lo(g), a1 = wk.lo(g + 1);
+    short f = 0;
+    if (a1 > a0 && a0 < u1 && a1 > u0) {
+      // the CTA's range [a0, a1) touches at most two tiles: slot 0 = the tile holding a0, slot 1 = the next one
+      f = (a0 / wk.nchunk == rt) ? 1 : 2;
     }
+    s_flag[g] = f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int g = 0; g < G && g < 1024; g++)
+      if (s_flag[g]) s_src[n++] = g * 2 + (s_flag[g] - 1);
     s_n = n;
   }
   __syncthreads();
   const int npieces = s_n, el = threadIdx.x & (VFX_ELEMS - 1), pl = threadIdx.x / VFX_ELEMS;
   const int e = blockIdx.y * VFX_ELEMS + el;
-  double sum = 0.0;
-  if (e < BM * BN)
-    for (int k = pl; k < npieces; k += 4) sum += p.sk_ws[(size_t)s_src[k] * ((size_t)BM * BN) + e];
-  part[pl][el] = sum;
+  double s0 = 0.0, s1 = 0.0;
+  if (e < BM * BN) {
+    const size_t tsz = (size_t)BM * BN;
+    int k = pl;
+    for (; k + VFX_LANES < npieces; k += 2 * VFX_LANES) {       // two independent loads in flight per step
+      const double v0 = p.sk_ws[(size_t)s_src[k] * tsz + e], v1 = p.sk_ws[(size_t)s_src[k + VFX_LANES] * tsz + e];
+      s0 += v0; s1 += v1;
+    }
+    if (k < npieces) s0 += p.sk_ws[(size_t)s_src[k] * tsz + e];
+  }
+  part[pl][el] = s0 + s1;
   __syncthreads();
   if (pl == 0 && e < BM * BN) {
     const int r = tr * BM + e / BN, col = tn * BN + e % BN;
     if (r < p.nk && col < p.ncols_d) {
-      const double tot = (part[0][el] + part[1][el]) + (part[2][el] + part[3][el]);
+      double tot = 0.0;
+#pragma unroll
+      for (int l = 0; l < VFX_LANES; l += 2) tot += part[l][el] + part[l + 1][el];      // fixed order: deterministic
       double *dst = p.out + (size_t)r * p.ncols_d + col;
       *dst = p.accumulate ? *dst + tot : tot;
     }
