@@ -724,11 +724,12 @@ __global__ void __launch_bounds__(NT_WS, 1) k_project_ws(const __grid_constant__
 #pragma unroll
       for (int b = 0; b < WN; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-    // RAG instantiation only: optional start-of-segment delay of consumer warps 4-7 (p.lag_ns, 0 = none: the default).
+    // RAG and EPI_PEER instantiations only: optional start-of-segment delay of consumer warps 4-7 (p.lag_ns, 0 = none: the default).
     // Measured: no gain from the delay itself, but with this statement in place ptxas gives the RAG kernel's
-    // main loop the 6257-cycle schedule instead of the 6338-cycle one (cfg3 71.1 -> 70.5 ms per element); the RAG = false
-    // kernel does not contain it and keeps its code.  tests/test_host_cpu.py guards both counts.
-    if (RAG && p.lag_ns != 0 && cw >= NCW / 2 && c1 - c0 >= 4) asm volatile("nanosleep.u32 %0;\n" ::"r"(p.lag_ns));
+    // main loop the 6257-cycle schedule instead of the 6338-cycle one (cfg3 71.1 -> 70.5 ms per element), and the fused
+    // multi-GPU kernel 6254 instead of 6308; the dense RAG = false kernel and the masked one (which it would slow: 6388) do
+    // not contain it and keep their code.  tests/test_host_cpu.py guards both counts.
+    if ((RAG || EPI == EPI_PEER) && p.lag_ns != 0 && cw >= NCW / 2 && c1 - c0 >= 4) asm volatile("nanosleep.u32 %0;\n" ::"r"(p.lag_ns));
 
     const int c1m = (RAG && c1 == nchunk) ? c1 - 1 : c1;     // RAG: the tile's last chunk is handled after the loop
     for (int c = c0; c < c1m; c++, it++) {
