@@ -180,18 +180,23 @@ def test_dense_dmma_loop_keeps_the_fast_ptxas_schedule():
     import shutil
     if not shutil.which("cuobjdump"):
         pytest.skip("cuobjdump not available")
+    tile = "Li2ELi12ELi8ELi1ELb0ELi0ELi4ELi1EEE"                        # Tile<2, 12, 8, 1, real, matrix, 4, 1>
     out = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "sass_loop_stats.py"),
-                                   "Li2ELi12ELi8ELi1ELb0ELi0ELi4ELi1EEELi0ELb0E"], text=True)     # dense, full last chunk
-    m = re.search(r"DMMA\s+(\d+)\s+static stall cycles/chunk\s+(\d+)", out)
-    assert m, out
-    assert int(m.group(1)) == 384                      # 16 k-steps (64-point stage) x 2 row tiles x 12 column tiles
-    assert int(m.group(2)) <= 6290, out                # 384 x 16 = 6144 is the floor; 6256 today (the slower schedule: >= 6300)
-    # the instantiation with the trimmed last chunk (point counts off the stage size, cfg3): 6338 as first written, 6257 with
-    # the (inactive) start-of-segment lag statement that only this instantiation contains (cfg3 71.1 -> 70.6 ms per element)
-    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "sass_loop_stats.py"),
-                                   "Li2ELi12ELi8ELi1ELb0ELi0ELi4ELi1EEELi0ELb1E"], text=True)
-    m = re.search(r"DMMA\s+(\d+)\s+static stall cycles/chunk\s+(\d+)", out)
-    assert m and int(m.group(1)) == 384 and int(m.group(2)) <= 6290, out
+                                   tile + "Li0ELb0E", tile + "Li0ELb1E", tile + "Li2ELb0E"], text=True)
+
+    def stats(suffix):
+        m = re.search(re.escape(tile + suffix) + r".*DMMA\s+(\d+)\s+static stall cycles/chunk\s+(\d+)", out)
+        assert m, out
+        return int(m.group(1)), int(m.group(2))
+
+    # dense, full last chunk: 16 k-steps (64-point stage) x 2 row tiles x 12 column tiles; 384 x 16 = 6144 is the floor,
+    # 6256 today (the slower schedule: >= 6300)
+    assert stats("Li0ELb0E")[0] == 384 and stats("Li0ELb0E")[1] <= 6290, out
+    # trimmed last chunk (point counts off the stage size, cfg3): 6338 as first written, 6257 with the (inactive)
+    # start-of-segment lag statement that only this and the next instantiation contain (cfg3 71.1 -> 70.6 ms per element)
+    assert stats("Li0ELb1E")[0] == 384 and stats("Li0ELb1E")[1] <= 6290, out
+    # fused multi-GPU epilogue (EPI_PEER): 6254 (6308 without the statement: 1.5 % at 8 GPUs)
+    assert stats("Li2ELb0E")[0] == 384 and stats("Li2ELb0E")[1] <= 6290, out
 
 
 def test_cpp_caller_example_builds_against_the_reference_headers():

@@ -29,12 +29,12 @@ def parse(text):
 
 
 def main():
-    pat = sys.argv[1] if len(sys.argv) > 1 else "k_project_ws"
+    pats = sys.argv[1:] if len(sys.argv) > 1 else ["k_project_ws"]      # any of these substrings (one cuobjdump pass)
     out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
     funcs = re.split(r"\n\s*Function : ", out)
     for f in funcs[1:]:
         name = f.split("\n", 1)[0]
-        if pat not in name:
+        if not any(pat in name for pat in pats):
             continue
         ins = parse(f)
         idx = [i for i, x in enumerate(ins) if "DMMA" in x[0]]
