@@ -199,6 +199,25 @@ def test_dense_dmma_loop_keeps_the_fast_ptxas_schedule():
     assert stats("Li2ELb0E")[0] == 384 and stats("Li2ELb0E")[1] <= 6290, out
 
 
+def test_hot_kernels_do_not_spill():
+    """Static guard (no GPU): the DMMA kernels hold their accumulators and fragments in registers; a local-memory frame in one of
+    them means ptxas spilled (seen twice during development: a `__noinline__` helper, a register-resident tail table)."""
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(ROOT, "pspace_b200", "lib", "libpspace_cuda.so")
+    out = subprocess.check_output(["cuobjdump", "-res-usage", lib], text=True)
+    seen = 0
+    for name, stack in re.findall(r"Function (\S+):\s*\n\s*REG:\d+ STACK:(\d+)", out):
+        if "k_project_ws" in name or "k_expand_f" in name:
+            seen += 1
+            assert int(stack) == 0, (name, stack)
+        elif "k_project_vf" in name:
+            seen += 1
+            assert int(stack) <= 16, (name, stack)      # two variants keep one 8/16-byte temporary
+    assert seen >= 40, seen
+
+
 def test_cpp_caller_example_builds_against_the_reference_headers():
     """examples/stochastic_element.cpp — a caller shaped like the reference's TACSStochasticElement — compiles and links
     against host/include + libpspace.so in both scalar builds, and (no CPU path) aborts loudly without a GPU."""
