@@ -54,16 +54,16 @@ class _Api:
             fn = getattr(self.lib, prefix + name + suffix)
             fn.restype, fn.argtypes = res, args
             setattr(self, name, fn)
+        fn = getattr(self.lib, prefix + "moments" + suffix)
+        fn.restype, fn.argtypes = None, [_vp, _i, _vp, _ll, _ll, _vp, _vp, _vp]
+        self.moments = fn
+        fn = getattr(self.lib, prefix + "adj_res_product" + suffix)
+        fn.restype, fn.argtypes = None, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]
+        self.adj_res_product = fn
         if prefix == "oracle_":
-            fn = getattr(self.lib, "oracle_moments" + suffix)
-            fn.restype, fn.argtypes = None, [_vp, _i, _vp, _ll, _ll, _vp, _vp, _vp]
-            self.moments = fn
             fn = getattr(self.lib, "oracle_project_matrix_qrange" + suffix)
             fn.restype, fn.argtypes = None, [_vp, _i, _vp, _i, _i, _i, _i, _ll, _ll, _vp, _i]
             self.project_matrix_qrange = fn
-            fn = getattr(self.lib, "oracle_adj_res_product" + suffix)
-            fn.restype, fn.argtypes = None, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]
-            self.adj_res_product = fn
             self.synthetic_adjres_element = ctypes.cast(getattr(self.lib, "oracle_synthetic_adjres_element" + suffix), _vp)
             fs = self.lib.oracle_fill_synthetic
             fs.restype, fs.argtypes = None, [_vp, _ll, ctypes.c_ulonglong, ctypes.c_ulonglong]

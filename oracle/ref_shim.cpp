@@ -177,4 +177,60 @@ void refshim_project_matrix(void *hh, int m2, const double *J_, int i0, int i1, 
   for (auto &t : th) t.join();
 }
 
+// (f3) moments of m function values per point over q in [q0,q1)  (TACSStochasticFunction.cpp:209-238 getFunctionValue):
+// fmean += wq*basis(0,zq)*f ; ffmean += wq*basis(0,zq)*f*f ; variance = ffmean - fmean*fmean.   f holds rows q0..q1-1.
+void refshim_moments(void *hh, int m, const double *f_, long long q0, long long q1, double *mean_, double *second_, double *var_){
+  RefHandle *h = (RefHandle*)hh;
+  const scalar *f = (const scalar*)f_; scalar *mean = (scalar*)mean_, *second = (scalar*)second_, *var = (scalar*)var_;
+  std::vector<scalar> zq(h->nvars), yq(h->nvars);
+  for (int c = 0; c < m; c++){ mean[c] = 0.0; second[c] = 0.0; }
+  for (long long q = q0; q < q1; q++){
+    scalar wq = h->pc->quadrature((int)q, zq.data(), yq.data());
+    scalar wb = wq*h->pc->basis(0, zq.data());
+    const scalar *fq = f + (size_t)(q-q0)*m;
+    for (int c = 0; c < m; c++){ mean[c] += wb*fq[c]; second[c] += wb*fq[c]*fq[c]; }
+  }
+  for (int c = 0; c < m; c++) var[c] = second[c] - mean[c]*mean[c];
+}
+
+// (f4) the loop of TACSStochasticElement::addAdjResProduct (examples/stacs/cpp/TACSStochasticElement.cpp:548-637) over
+// the reference's primitives: for j = 0 (:583), for q: wq = quadrature(q,zq,yq); wt = basis(j,zq)*wq; deterministic
+// states / adjoint from the TACS-interleaved stochastic vectors (getDeterministicStates :84-120, getDeterministicAdjoint
+// :53-82); the deterministic element (TACS is not vendored: a callback with the oracle's signature) adds into dfdxj with
+// weight wt*scale; dfdx[n] += dfdxj[n].
+typedef void (*adjres_element)(void *user, const double *scale, const double *psi, const double *u, const double *y,
+                               int m, int nvars, int dvlen, double *dfdx);
+void refshim_adj_res_product(void *hh, int nnodes, int ndvpn, int dvlen, const double *scale_, const double *v_,
+                             const double *adj_, adjres_element elem, void *user, double *dfdx_){
+  RefHandle *h = (RefHandle*)hh;
+  const scalar scale = *(const scalar*)scale_;
+  const scalar *v = (const scalar*)v_, *adj = (const scalar*)adj_;
+  scalar *dfdx = (scalar*)dfdx_;
+  const int nsterms = h->pc->getNumBasisTerms(), nsvpn = nsterms*ndvpn, nddof = nnodes*ndvpn;
+  const int nqpts = h->pc->getNumQuadraturePoints();
+  std::vector<scalar> zq(h->nvars), yq(h->nvars), uq(nddof), psiq(nddof), dfdxj(dvlen);
+  for (int j = 0; j < 1; j++){
+    for (int n = 0; n < dvlen; n++) dfdxj[n] = 0.0;
+    for (int q = 0; q < nqpts; q++){
+      scalar wq = h->pc->quadrature(q, zq.data(), yq.data());
+      scalar wt = h->pc->basis(j, zq.data())*wq;
+      for (int c = 0; c < nddof; c++){ uq[c] = 0.0; psiq[c] = 0.0; }
+      for (int n = 0; n < nnodes; n++){
+        for (int k = 0; k < nsterms; k++){
+          scalar psikz = h->pc->basis(k, zq.data());
+          int lptr = n*ndvpn, gptr = n*nsvpn + k*ndvpn;
+          for (int d = 0; d < ndvpn; d++){
+            uq[lptr+d] += v[gptr+d]*psikz;
+            psiq[lptr+d] += adj[gptr+d]*psikz;
+          }
+        }
+      }
+      scalar ws = wt*scale;
+      elem(user, (const double*)&ws, (const double*)psiq.data(), (const double*)uq.data(), (const double*)yq.data(),
+           nddof, h->nvars, dvlen, (double*)dfdxj.data());
+    }
+    for (int n = 0; n < dvlen; n++) dfdx[n] += dfdxj[n];
+  }
+}
+
 } // extern "C"

@@ -75,6 +75,36 @@ def test_projection_loops_bit_exact(cplx):
     assert np.max(np.abs(Ca + Cb - cr.project_matrix(J))) < 1e-14
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+def test_moments_and_adjoint_product_loops_bit_exact(cplx):
+    """(f3) getFunctionValue moments and (f4) addAdjResProduct: the oracle's restated loops against the same loops driven by the
+    compiled reference's quadrature() / basis() (oracle/ref_shim.cpp), with the same synthetic deterministic element."""
+    rng = np.random.default_rng(123)
+    o, r = H.oracle_api(cplx), H.ref_api(cplx)
+    ps = [("normal", 0.3 + (1e-30j if cplx else 0), 1.2, 2), ("exponential", 0.0, 0.5, 3), ("uniform", -1.0, 2.0, 2)]
+    co = H.CpuContainer(o, ps, 1).initialize()
+    cr = H.CpuContainer(r, ps, 1).initialize()
+    f = rng.normal(size=(co.Q, 5)).astype(co.dtype)
+    if cplx:
+        f = f + 1j * rng.normal(size=f.shape)
+    for (q0, q1) in ((0, co.Q), (3, 20)):
+        for a, b in zip(co.moments(f[q0:q1], q0, q1), cr.moments(f[q0:q1], q0, q1)):
+            assert same_bits(a, b)
+    nnodes, ndvpn, dvlen = 3, 2, 7
+    v = rng.normal(size=nnodes * co.N * ndvpn).astype(co.dtype)
+    adj = rng.normal(size=v.size).astype(co.dtype)
+    if cplx:
+        v = v + 1j * rng.normal(size=v.size)
+        adj = adj - 0.5j * rng.normal(size=v.size)
+    elem = o.synthetic_adjres_element                    # one element implementation for both arms (a C callback)
+    a = co.adj_res_product(v, adj, nnodes, ndvpn, dvlen, 0.7, element=elem)
+    b = cr.adj_res_product(v, adj, nnodes, ndvpn, dvlen, 0.7, element=elem)
+    assert same_bits(a, b) and np.all(np.isfinite(a.view(np.float64))) and np.any(a != 0)
+    base = rng.normal(size=dvlen).astype(co.dtype)
+    assert same_bits(co.adj_res_product(v, adj, nnodes, ndvpn, dvlen, 1.0, element=elem, dfdx=base.copy()),
+                     cr.adj_res_product(v, adj, nnodes, ndvpn, dvlen, 1.0, element=elem, dfdx=base.copy()))
+
+
 def test_high_degree_single_variable_bit_exact():
     """d up to 15: factorial loop (n > 10), deep naive recursions, Legendre pow sum."""
     for cplx in (False, True):
