@@ -249,12 +249,13 @@ def tacs_scatter_matrix(C, nnodes, ndvpn, mat=None):
     return mat
 
 
-def pair_mask(deg, dmapf):
+def pair_mask(deg, dmapf, reference=False):
+    """nonzero() pair filter on a degree table; reference=True: through the compiled reference's BasisHelper::sparse."""
     deg = np.ascontiguousarray(deg, dtype=np.intc)
     dm = np.ascontiguousarray(dmapf, dtype=np.intc)
     N, nv = deg.shape
     mask = np.zeros((N, N), dtype=np.uint8)
-    lib = oracle_api(False).lib
-    lib.oracle_pair_mask.argtypes = [_i, _i, _vp, _vp, _vp]
-    lib.oracle_pair_mask(N, nv, _ptr(deg), _ptr(dm), _ptr(mask))
+    fn = ref_api(False).lib.refshim_pair_mask if reference else oracle_api(False).lib.oracle_pair_mask
+    fn.restype, fn.argtypes = None, [_i, _i, _vp, _vp, _vp]
+    fn(N, nv, _ptr(deg), _ptr(dm), _ptr(mask))
     return mask

@@ -24,6 +24,7 @@
 #include "scalar.h"
 #include "ParameterFactory.h"
 #include "ParameterContainer.h"
+#include "BasisHelper.h"
 
 struct RefHandle {
   ParameterFactory *factory;      // one factory per container (ids restart at 0)
@@ -231,6 +232,24 @@ void refshim_adj_res_product(void *hh, int nnodes, int ndvpn, int dvlen, const d
     }
     for (int n = 0; n < dvlen; n++) dfdx[n] += dfdxj[n];
   }
+}
+
+// (f2) basis-pair filter: the reference library's own BasisHelper::sparse (BasisHelper.cpp:76-88) per variable, combined as
+// the caller's nonzero() does (TACSStochasticElement.cpp:7-21: product of the per-variable flags), on a degree table [N][nvars]
+void refshim_pair_mask(int N, int nvars, const int *deg, const int *dmapf, unsigned char *mask){
+  BasisHelper bh(0);
+  std::vector<int> di(nvars), dj(nvars), dk(dmapf, dmapf + nvars);
+  bool *flt = new bool[nvars];
+  for (int i = 0; i < N; i++){
+    for (int j = 0; j < N; j++){
+      for (int d = 0; d < nvars; d++){ di[d] = deg[i*nvars + d]; dj[d] = deg[j*nvars + d]; }
+      bh.sparse(nvars, di.data(), dj.data(), dk.data(), flt);
+      int prod = 1;
+      for (int d = 0; d < nvars; d++) prod *= flt[d] ? 1 : 0;
+      mask[(size_t)i*N + j] = (unsigned char)prod;
+    }
+  }
+  delete [] flt;
 }
 
 } // extern "C"

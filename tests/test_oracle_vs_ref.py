@@ -105,6 +105,18 @@ def test_moments_and_adjoint_product_loops_bit_exact(cplx):
                      cr.adj_res_product(v, adj, nnodes, ndvpn, dvlen, 1.0, element=elem, dfdx=base.copy()))
 
 
+def test_pair_filter_equals_the_reference_library_function():
+    """(f2) nonzero() filter: the oracle's restatement against BasisHelper::sparse of the compiled reference, on the degree
+    tables of tensor and complete bases with uniform and per-variable integrand degrees."""
+    o = H.oracle_api(False)
+    for bt, dmax in ((0, [3, 2, 4]), (1, [4, 4, 4, 4]), (1, [2, 5])):
+        ps = [("normal", 0.0, 1.0, d) for d in dmax]
+        deg = H.CpuContainer(o, ps, bt).initialize().degrees()
+        for dmapf in ([0] * len(dmax), [1] * len(dmax), [3] * len(dmax), list(range(len(dmax)))):
+            a, b = H.pair_mask(deg, dmapf), H.pair_mask(deg, dmapf, reference=True)
+            assert np.array_equal(a, b) and a.any() and (dmapf[0] >= max(dmax) or not a.all())
+
+
 def test_high_degree_single_variable_bit_exact():
     """d up to 15: factorial loop (n > 10), deep naive recursions, Legendre pow sum."""
     for cplx in (False, True):
