@@ -599,7 +599,7 @@ def run_b200(args):
                                + "; the largest is the denominator (MEASURED_PEAKS.json has no FP64 figure; bf16 peak does not apply to an FP64 path)",
                 "kernel_ms": kms, "flop_per_launch": flop_launch,
                 "note": "event time spans the whole project call" + (f" ({nE} elements)" if batched else "") +
-                        ": 2 basis-panel kernels + k_project_ws + k_fixup; useful FLOP only (fragment DMULs and padded tile rows are not counted)"}
+                        ": basis-panel kernel (one launch for a square window, else two) + k_project_ws + k_fixup; useful FLOP only (fragment DMULs and padded tile rows are not counted)"}
 
     cpu = None
     if not args.no_cpu and world == 1:
