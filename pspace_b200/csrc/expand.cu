@@ -187,7 +187,7 @@ template <int WM_, int WN_, bool CPLX_, int KC_> struct XTile {
   static constexpr int W = CPLX ? 2 : 1;
   static constexpr int BQ = XNCW * WM * 8, BN = WN * 8, LDB = BN + 4;
   static constexpr int KC = KC_;                   // basis rows per pipeline stage (128, 64 or 32)
-  static constexpr int KCP = KC + 4;               // == 4 (mod 16): conflict-free S reads (row g -> consecutive tail points)
+  static constexpr int KCP = KC + 8;               // == 8 (mod 16): conflict-free 16-byte S reads (rows g, g+1 -> banks 0-15, 16-31)
   static constexpr int TPR = XNPT / KC;            // producer threads per basis row
   static constexpr int V_BYTES = KC * LDB * 8;
   static_assert(LDB % 16 == 4 || LDB % 16 == 12, "V pitch");
@@ -195,8 +195,8 @@ template <int WM_, int WN_, bool CPLX_, int KC_> struct XTile {
   __host__ __device__ static size_t eo_bytes(int nvars, int nkc, int res) {
     return ((size_t)(res ? nkc * KC : TPR * KC) * nvars * 2 + 15) & ~(size_t)15;
   }
-  __host__ __device__ static size_t tab_bytes(int tsz) { return tsz <= psf::TAB_SMEM_MAX ? (size_t)tsz * W * 8 : 0; }
-  __host__ __device__ static size_t sres_bytes(int L, int nkc, int res) { return res ? (size_t)W * L * (nkc * KC + 4) * 8 : 0; }
+  __host__ __device__ static size_t tab_bytes(int tsz) { return tsz <= psf::TAB_SMEM_MAX ? (((size_t)tsz * W * 8 + 15) & ~(size_t)15) : 0; }   // S_res behind it is read with 16-byte loads
+  __host__ __device__ static size_t sres_bytes(int L, int nkc, int res) { return res ? (size_t)W * L * (nkc * KC + 8) * 8 : 0; }
   __host__ __device__ static size_t header_bytes(int nvars, int tsz, int L, int nkc, int res) {
     return (eo_bytes(nvars, nkc, res) + tab_bytes(tsz) + sres_bytes(L, nkc, res) + 127) / 128 * 128;
   }
@@ -205,13 +205,17 @@ template <int WM_, int WN_, bool CPLX_, int KC_> struct XTile {
   }
 };
 
+// Column of basis row r in the S / P tables: inside each group of 8 rows, rows kl and kl + 4 — the A-fragment elements one thread
+// needs for two consecutive k-steps — sit side by side, so that one 16-byte load serves both k-steps.
+__device__ __forceinline__ int xf_col(int r) { return (r & ~7) | ((r & 3) << 1) | ((r >> 2) & 1); }
+
 template <class TL>
 __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFParams p, const __grid_constant__ CUtensorMap tmapV) {
   constexpr int WM = TL::WM, WN = TL::WN, W = TL::W, BQ = TL::BQ, BN = TL::BN, LDB = TL::LDB, KC = TL::KC, KCP = TL::KCP;
   constexpr bool CPLX = TL::CPLX;
   constexpr bool PAIRED = CPLX && (WN % 2) == 0;
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int RES = p.resident, NR = p.nkc * KC, NRP = NR + 4;
+  const int RES = p.resident, NR = p.nkc * KC, NRP = NR + 8;
   unsigned short *eo_all = reinterpret_cast<unsigned short *>(smem);        // resident: [nvars][NR]; else [TPR][nvars][KC]
   double *Ts = reinterpret_cast<double *>(smem + TL::eo_bytes(p.nvars, p.nkc, RES));
   double *S_res = reinterpret_cast<double *>(smem + TL::eo_bytes(p.nvars, p.nkc, RES) + TL::tab_bytes(p.tsz));   // [W][L][NRP]
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
       const bool valid = r < p.nk;
       for (int d = 0; d < p.nvars; d++)
         eo_all[d * NR + r] = (unsigned short)(valid ? p.toff[d] + __ldg(p.deg + (size_t)(p.k0 + r) * p.nvars + d) * p.nq[d] : 0);
-      run_products<CPLX>(p.T, eo_all + r, NR, p.qdig, p.DP, 0, p.L, 1, p.Qtot, p.dsplit, p.nvars, nq_tail, valid, S_res + r, NRP, p.L);
+      run_products<CPLX>(p.T, eo_all + r, NR, p.qdig, p.DP, 0, p.L, 1, p.Qtot, p.dsplit, p.nvars, nq_tail, valid, S_res + xf_col(r), NRP, p.L);
     }
   }
   __syncthreads();
@@ -289,12 +293,12 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
         if (e_lo < p.npfx) {
           const int n = min(e_hi, p.npfx) - e_lo;
           run_products<CPLX>(T, eo, eos, p.qdig, p.DP, blk0 + e_lo, n, p.L, p.Qtot, 0, p.dsplit, nq_pfx, valid,
-                             Pst + e_lo * KCP + r, KCP, p.npfx);
+                             Pst + e_lo * KCP + xf_col(r), KCP, p.npfx);
         }
         if (e_hi > p.npfx) {
           const int t0 = max(e_lo, p.npfx) - p.npfx, n = e_hi - p.npfx - t0;
           run_products<CPLX>(T, eo, eos, p.qdig, p.DP, t0, n, 1, p.Qtot, p.dsplit, p.nvars, nq_tail, valid,
-                             Sst + t0 * KCP + r, KCP, p.L);
+                             Sst + t0 * KCP + xf_col(r), KCP, p.L);
         }
         mbar_arrive(&full[s]);
         if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -325,8 +329,8 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
         for (int a = 0; a < WM; a++) {
           const int r = r0 + min(warp * (WM * 8) + a * 8 + g, rmax);
           const int b = r / p.L;
-          soff[a] = (r - b * p.L) * spitch + kl;
-          poff[a] = b * KCP + kl;
+          soff[a] = (r - b * p.L) * spitch + 2 * kl;
+          poff[a] = b * KCP + 2 * kl;
         }
       }
       double acc[WM][WN][2];
@@ -345,48 +349,65 @@ __global__ void __launch_bounds__(XFT, 1) k_expand_f(const __grid_constant__ XFP
         const double *Pr = reinterpret_cast<const double *>(st + P_OFF), *Pi = Pr + (size_t)p.npfx * KCP;
         const int ksteps = (min(KC, p.nk - kc * KC) + 3) >> 2;
         int depi = 0;
-        auto kstep = [&](const int ks) {
-          double are[WM], aim[WM];
+        // one step = TWO k-steps.  Real scalars: the S and P elements of both come from one 16-byte load each (see xf_col);
+        // the complex build (twice the fragment registers) reads them per k-step from the same layout.
+        auto kpair = [&](const int kp) {
+          double are[2][WM], aim[CPLX ? 2 : 1][CPLX ? WM : 1];
+          if (!CPLX) {
 #pragma unroll
-          for (int a = 0; a < WM; a++) {
-            const double sr = Sr[soff[a] + ks * 4], pr = Pr[poff[a] + ks * 4];
-            if (!CPLX) are[a] = sr * pr;
-            else {
-              const double si = Si[soff[a] + ks * 4], pi = Pi[poff[a] + ks * 4];
-              are[a] = sr * pr - si * pi;
-              aim[a] = sr * pi + si * pr;
-            }
-          }
-          double bfr[WN], bsw[WN];
-          if (PAIRED) {
-#pragma unroll
-            for (int b2 = 0; b2 < WN / 2; b2++) {
-              const double2 v = *reinterpret_cast<const double2 *>(bs2 + ks * 4 * LDB + 16 * b2);
-              bfr[2 * b2] = v.x; bfr[2 * b2 + 1] = v.y;
-              if (CPLX) { bsw[2 * b2] = flip_sign(v.y, 0x80000000u); bsw[2 * b2 + 1] = v.x; }
-            }
-          } else {
-#pragma unroll
-            for (int b = 0; b < WN; b++) {
-              bfr[b] = bs[ks * 4 * LDB + b * 8];
-              if (CPLX) bsw[b] = flip_sign(bs[ks * 4 * LDB + b * 8 + ((g & 1) ? -1 : 1)], sgn);
+            for (int a = 0; a < WM; a++) {
+              const double2 sr = *reinterpret_cast<const double2 *>(Sr + soff[a] + kp * 8);
+              const double2 pr = *reinterpret_cast<const double2 *>(Pr + poff[a] + kp * 8);
+              are[0][a] = sr.x * pr.x; are[1][a] = sr.y * pr.y;
             }
           }
 #pragma unroll
-          for (int a = 0; a < WM; a++)
+          for (int e = 0; e < 2; e++) {
+            const int ks = 2 * kp + e;
+            if (CPLX) {
 #pragma unroll
-            for (int b = 0; b < WN; b++) {
-              dmma884(acc[a][b][0], acc[a][b][1], are[a], bfr[b]);
-              if (CPLX) dmma884(acc[a][b][0], acc[a][b][1], aim[a], bsw[b]);
+              for (int a = 0; a < WM; a++) {
+                const double sr = Sr[soff[a] + kp * 8 + e], pr = Pr[poff[a] + kp * 8 + e];
+                const double si = Si[soff[a] + kp * 8 + e], pi = Pi[poff[a] + kp * 8 + e];
+                are[e][a] = sr * pr - si * pi;
+                aim[CPLX ? e : 0][CPLX ? a : 0] = sr * pi + si * pr;
+              }
             }
-          depi = __double2loint(are[WM - 1]) ^ __double2loint(bfr[WN - 1]);
+            double bfr[WN], bsw[WN];
+            if (PAIRED) {
+#pragma unroll
+              for (int b2 = 0; b2 < WN / 2; b2++) {
+                const double2 v = *reinterpret_cast<const double2 *>(bs2 + ks * 4 * LDB + 16 * b2);
+                bfr[2 * b2] = v.x; bfr[2 * b2 + 1] = v.y;
+                if (CPLX) { bsw[2 * b2] = flip_sign(v.y, 0x80000000u); bsw[2 * b2 + 1] = v.x; }
+              }
+            } else {
+#pragma unroll
+              for (int b = 0; b < WN; b++) {
+                bfr[b] = bs[ks * 4 * LDB + b * 8];
+                if (CPLX) bsw[b] = flip_sign(bs[ks * 4 * LDB + b * 8 + ((g & 1) ? -1 : 1)], sgn);
+              }
+            }
+#pragma unroll
+            for (int a = 0; a < WM; a++)
+#pragma unroll
+              for (int b = 0; b < WN; b++) {
+                dmma884(acc[a][b][0], acc[a][b][1], are[e][a], bfr[b]);
+                if (CPLX) dmma884(acc[a][b][0], acc[a][b][1], aim[CPLX ? e : 0][CPLX ? a : 0], bsw[b]);
+              }
+            depi = __double2loint(are[e][WM - 1]) ^ __double2loint(bfr[WN - 1]);
+          }
         };
-        if (ksteps == KC / 4) {
+        const int kpairs = (ksteps + 1) >> 1;          // an odd k-step count runs one more k-step of zero rows
+        if (kpairs == KC / 8) {
 #pragma unroll
-          for (int ks = 0; ks < KC / 4; ks++) kstep(ks);      // full chunk: one straight-line block, loads hoisted across k-steps
+          for (int kp = 0; kp < KC / 8; kp++) kpair(kp);      // full chunk: one straight-line block, loads hoisted across k-steps
+        } else if (kpairs == KC / 16) {
+#pragma unroll
+          for (int kp = 0; kp < KC / 16; kp++) kpair(kp);     // half chunk, also straight-line (cfg5: 286 rows = 4 x 64 + 30)
         } else {
 #pragma unroll 2
-          for (int ks = 0; ks < ksteps; ks++) kstep(ks);
+          for (int kp = 0; kp < kpairs; kp++) kpair(kp);
         }
         // release the stage: the arrive's address depends on the last fragment registers read from it
         const unsigned dep = (unsigned)depi & p.zero;
